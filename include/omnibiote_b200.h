@@ -1,0 +1,144 @@
+/*
+ * omnibiote_b200 — C ABI of the B200 (sm_100a) kernels behind the OmniBioTA encoder hot path.
+ *
+ * The reference (nyuolab/OmniBioTE) has no native/FFI layer: its boundary is the Python class API of
+ * training/model.py, and every device op is a PyTorch library call. Each entry point below therefore cites the
+ * reference Python line(s) whose computation it replaces. The Python module omnibiote_b200/model.py mirrors the
+ * reference classes and calls these functions through ctypes with raw device pointers and the current CUDA stream.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all tensors are bf16 (uint16 storage) unless stated; row-major.
+ *  - the caller owns every buffer (including workspaces); the library never allocates or frees device memory and
+ *    keeps no reference to caller buffers (the only global state is a mutex-guarded TMA-descriptor cache).
+ *  - every function enqueues on `stream` and returns immediately: 0 on success, negative on error
+ *    (-1 invalid argument, -2 CUDA error, -3 unsupported); obt_last_error() returns a thread-local message.
+ *  - no CPU fallback: pointers must be device pointers on the current device.
+ *  - rb(x) below = round-to-nearest-even to bf16.
+ */
+#ifndef OMNIBIOTE_B200_H_
+#define OMNIBIOTE_B200_H_
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* obt_last_error(void);
+int obt_version(void);
+void obt_clear_descriptor_cache(void);
+
+/* ---- GEMM (tcgen05 / TMEM / TMA) ------------------------------------------------------------------------------
+ * D[M,N] = epilogue( op(A)[M,K] * op(B)[N,K]^T ), fp32 accumulation.
+ *   a_mn_major = 0: A stored [M][K] (pitch lda)   = 1: A stored [K][M] (pitch lda)
+ *   b_mn_major = 0: B stored [N][K] (pitch ldb)   = 1: B stored [K][N] (pitch ldb)
+ * Replaces nn.Linear forward (model.py:102,151,163,166; MuReadout model.py:208,253) = (0,0);
+ * its input gradient (autograd, train_encoder.py:308) = (0,1); its weight gradient = (1,1).
+ * epilogue: 0 plain rb(acc)
+ *           1 D = rb(aux_in + rb(acc))                 residual add (model.py:179-180) / .grad accumulation
+ *           2 aux_out = U = rb(acc); D = rb(gelu(U))   fused_gelu (model.py:23-25)
+ *           3 D = rb(rb(acc) * gelu'(aux_in))          backward of fused_gelu, aux_in = U
+ *           5 D = rb(aux_in + dropout(rb(acc)))        resid_dropout + residual (model.py:151,167,179-180)
+ * gelu_mode: 0 = single rounding (TorchScript-fused execution), 1 = one bf16 rounding per primitive (eager CPU).
+ * workspace (fp32, optional): enables split-K for small-output / long-reduction shapes (weight gradients).
+ */
+void obt_gemm_set_cta_group(int cta_group); /* 0 auto, 1 or 2 forced (tests, ablations) */
+long long obt_gemm_workspace_elems(long long M, long long N, long long K);
+int obt_gemm_bf16(const void* A, const void* B, void* D, long long M, long long N, long long K, long long lda,
+                  long long ldb, long long ldd, int a_mn_major, int b_mn_major, int epilogue, const void* aux_in,
+                  long long ld_aux_in, void* aux_out, long long ld_aux_out, int gelu_mode, float drop_p,
+                  unsigned long long seed, unsigned long long offset, void* workspace, long long workspace_elems,
+                  cudaStream_t stream);
+
+/* ---- embedding: nn.Embedding + nn.Dropout(inplace) (model.py:241-242) ----------------------------------------- */
+int obt_embed_fwd(const long long* idx, const void* wte, void* out, long long M, int C, int V, float drop_p,
+                  unsigned long long seed, unsigned long long offset, int* err_flag, cudaStream_t stream);
+/* dense (V,C) gradient like embedding_dense_backward; scratch fp32 [V*C] and touched int32 [V] must be zero on
+ * entry and are zero again on exit. */
+int obt_embed_bwd(const long long* idx, const void* dout, void* dwte, float* scratch, int* touched, long long M, int C,
+                  int V, int accumulate, float drop_p, unsigned long long seed, unsigned long long offset,
+                  cudaStream_t stream);
+
+/* ---- LayerNorm: F.layer_norm(x, (C,), weight, None, 1e-5) (model.py:63-72) -------------------------------------
+ * z (optional) = rb(y / readout_div): the MuReadout input scaling x / width_mult (mup MuReadout.forward). */
+int obt_layernorm_fwd(const void* x, const void* gamma, void* y, void* z, float* mean, float* rstd, long long M, int C,
+                      float eps, float readout_div, cudaStream_t stream);
+int obt_layernorm_bwd_workspace_rows(void);
+/* dx = rb(dres + rb(ln_bwd(rb(dy / dy_div)))); dgamma (+)= rb(sum_rows dy * xhat). workspace fp32 [rows*C]. */
+int obt_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                      const void* dres, void* dx, void* dgamma, int accumulate_dgamma, float* workspace, long long M,
+                      int C, float dy_div, cudaStream_t stream);
+
+/* ---- rotary embedding, in place on the q and k column ranges of the fused qkv buffer (model.py:39-50,108) ------
+ * sin_tab == NULL: bf16 model whose complex freqs_cis buffer was cast to a real bf16 table (cosine scaling).
+ * tables are fp32 [>=T][head_dim/2]. inverse != 0 applies the adjoint (backward). */
+int obt_rope(void* qkv, const float* cos_tab, const float* sin_tab, long long M, int T, int C, int head_dim,
+             long long ld, int inverse, cudaStream_t stream);
+
+/* ---- dropout (nn.Dropout): out = keep ? rb(in/(1-p)) : 0, mask defined by (seed, offset, flat index) ---------- */
+int obt_dropout(const void* in, void* out, long long n, float p, unsigned long long seed, unsigned long long offset,
+                cudaStream_t stream);
+
+/* ---- MuReadout input scaling: out = rb(in / div), div = width_mult / output_mult (mup MuReadout.forward) ------- */
+int obt_scale_div(const void* in, void* out, long long n, float div, cudaStream_t stream);
+
+/* ---- encode() pooling (model.py:269-278): mode 0 = mean over T, 1 = max over T -------------------------------- */
+int obt_pool_splits(int T);
+int obt_pool(const void* emb, void* out, float* workspace, int B, int T, int C, int mode, cudaStream_t stream);
+int obt_pool_bwd(const void* emb, const void* pooled, const void* dout, void* demb, int B, int T, int C, int mode,
+                 cudaStream_t stream);
+
+/* ---- attention: F.scaled_dot_product_attention(q,k,v,attn_mask,dropout_p,scale=8/n_embd) (model.py:111-138) ---
+ * q,k,v are column ranges of the fused qkv buffer (row pitch ld); y is written head-major into [M, ldy] so the
+ * transpose+contiguous of model.py:148 disappears. mask: additive bf16, element (b,h,i,j) at
+ * mask[b*msb + h*msh + i*msq + j] (msh = 0 for the head-expanded view of train_encoder.py:292), or NULL.
+ * row_lo/row_hi (optional, instead of mask): per (b,i) visible key interval; lo >= hi marks a fully-masked row
+ * (uniform attention). lse: fp32 [B,H,T,2] = (row max, log exp-sum). */
+int obt_attn_simt_fwd(const void* q, const void* k, const void* v, long long ld, const void* mask, long long msb,
+                      long long msh, long long msq, const int* row_lo, const int* row_hi, void* y, long long ldy,
+                      float* lse, int B, int H, int T, int d, float scale, float drop_p, unsigned long long seed,
+                      unsigned long long offset, cudaStream_t stream);
+int obt_attn_simt_bwd(const void* q, const void* k, const void* v, long long ld, const void* mask, long long msb,
+                      long long msh, long long msq, const int* row_lo, const int* row_hi, const void* y, long long ldy,
+                      const void* dy, long long lddy, const float* lse, float* delta, void* dq, void* dk, void* dv,
+                      long long ldd, int B, int H, int T, int d, float scale, float drop_p, unsigned long long seed,
+                      unsigned long long offset, cudaStream_t stream);
+
+/* ---- attention-mask producers / compressors (input contract of the hot path) ------------------------------------
+ * obt_doc_mask_intervals : per (b,i) visible key interval [lo,hi) from token ids = create_attention_mask
+ *                          (train_encoder.py:25-57) incl. its quirks; lo >= hi marks a fully-masked row.
+ * obt_pad_mask_intervals : pad_attn (evals/gue.py:15-21).
+ * obt_mask_from_intervals: dense additive bf16 (B,T,T) {0,-1e9} tensor (what train_encoder.py:290-291 builds).
+ * obt_mask_compress      : dense additive mask (strides msb, msq, 1) -> intervals; *not_interval (pre-zeroed device
+ *                          int) is set when the mask is not exactly interval-structured. */
+int obt_doc_mask_intervals(const long long* ids, int* lo, int* hi, int B, int T, long long eos_token, int padding,
+                           cudaStream_t stream);
+int obt_pad_mask_intervals(const long long* ids, int* lo, int* hi, int B, int T, long long pad_token,
+                           cudaStream_t stream);
+int obt_mask_from_intervals(const int* lo, const int* hi, void* mask, int B, int T, cudaStream_t stream);
+int obt_mask_compress(const void* mask, long long msb, long long msq, int* lo, int* hi, int* not_interval, int B, int T,
+                      cudaStream_t stream);
+
+/* ---- MLM loss (train_encoder.py:301-305) over materialised logits ----------------------------------------------
+ * scalars (device fp32[4]): [0] loss, [1] number of masked tokens, [2] d loss / d CE_t. row_mask: uint8 [M] or NULL. */
+int obt_ce_fwd(const void* logits, long long ld, const long long* targets, const unsigned char* row_mask, float* lse,
+               float* tok_loss, float* scalars, long long M, int V, float n_acc, cudaStream_t stream);
+/* overwrites logits with d loss / d logits (exact zeros on unmasked rows) */
+int obt_ce_bwd(void* logits, long long ld, const long long* targets, const unsigned char* row_mask, const float* lse,
+               const float* scalars, float upstream, long long M, int V, cudaStream_t stream);
+
+/* ---- clip_grad_norm_ (train_encoder.py:316) + MuAdamW step (train_encoder.py:199,317) --------------------------
+ * metas: device array of {void* p, g, m, v; int64 numel; float lr, wd} (obt_opt_meta_bytes() each);
+ * blk_tensor/blk_off: one entry per block of obt_opt_chunk_elems() elements. */
+int obt_opt_chunk_elems(void);
+int obt_opt_meta_bytes(void);
+int obt_grad_norm(const void* metas, const int* blk_tensor, const long long* blk_off, int n_blocks, float gscale,
+                  float max_norm, float* partial, float* norm_out, cudaStream_t stream);
+int obt_adamw_step(const void* metas, const int* blk_tensor, const long long* blk_off, int n_blocks,
+                   const float* clip_scalars, float gscale, float lr_mult, float beta1, float beta2, float eps, int step,
+                   int zero_grad, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMNIBIOTE_B200_H_ */

@@ -1,0 +1,547 @@
+// bf16 GEMM on tcgen05 tensor cores for sm_100a:  D[M,N] (+)= op(A)[M,K] * op(B)[N,K]^T, fp32 accumulation in TMEM.
+//
+// Replaces every nn.Linear forward / dgrad / wgrad of the reference encoder block
+// (training/model.py:102 c_attn, :151 attn c_proj, :163 c_fc, :166 mlp c_proj, :253 lm_head via MuReadout).
+//
+// Design (one persistent CTA per SM, or one CTA pair per 2 SMs with cta_group::2):
+//   warp 0      : TMA producer  - cp.async.bulk.tensor tiles into a 128B-swizzled smem ring (mbarrier full/empty)
+//   warp 1      : MMA issuer    - one thread issues tcgen05.mma (128|256 x 256 x 16), accumulators in TMEM,
+//                                 2 accumulator stages (2 x 256 columns) so the epilogue overlaps the next tile
+//   warps 2..5  : epilogue      - tcgen05.ld (row per thread) -> fused epilogue -> vectorised global stores
+// Operand layouts: either operand may be K-major (K contiguous in memory) or MN-major (M/N contiguous), which covers
+// forward (K,K), dgrad (K,MN) and wgrad (MN,MN) without materialising transposes.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace obt {
+
+enum : int {
+  EPI_PLAIN = 0,     // D = rb(acc)
+  EPI_RESID = 1,     // D = rb(float(aux_in) + float(rb(acc)))            (residual add / gradient accumulation)
+  EPI_GELU = 2,      // aux_out = U = rb(acc); D = rb(gelu(U))             (model.py:23-25,163-165)
+  EPI_GELU_BWD = 3,  // D = rb(float(rb(acc)) * gelu'(float(aux_in)))      (aux_in = U saved by EPI_GELU)
+  EPI_PARTIAL = 4,   // split-K: fp32 partial tile -> workspace[split]
+  EPI_RESID_DROPOUT = 5,  // D = rb(float(aux_in) + float(rb(rb(acc) * keep/(1-p))))   (resid_dropout, model.py:151,167)
+};
+
+struct GemmParams {
+  int M, N, K;
+  int num_m, num_n, splits, kb_per_split, num_kb;
+  int epi, gelu_mode, vec_ok;
+  __nv_bfloat16* D;
+  long long ldd;
+  const __nv_bfloat16* aux_in;
+  long long ld_aux_in;
+  __nv_bfloat16* aux_out;
+  long long ld_aux_out;
+  float* partial;
+  float drop_p;
+  unsigned long long seed, offset;
+};
+
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_BN = 256;
+constexpr int GEMM_BM_CTA = 128;
+constexpr int GEMM_GROUP_M = 16;
+
+__device__ __forceinline__ float gelu_ref(float x, int mode) {
+  // reference: x * 0.5 * (1.0 + erf(x / 1.41421))  -- the constant is 1.41421, not sqrt(2) (model.py:25)
+  if (mode == 0) return x * 0.5f * (1.0f + erff(x / 1.41421f));
+  // per-primitive bf16 rounding (un-fused TorchScript / CPU eager execution of the same expression)
+  float a = rb(x * 0.5f);
+  float b = rb(x / 1.41421f);
+  float c = rb(erff(b));
+  float d = rb(1.0f + c);
+  return a * d;  // caller rounds
+}
+
+__device__ __forceinline__ float gelu_grad_ref(float x) {
+  const float inv = 1.0f / 1.41421f;
+  float t = x * inv;
+  float cdf = 0.5f * (1.0f + erff(t));
+  // d/dx erf(x/c) = 2/sqrt(pi) * exp(-(x/c)^2) / c
+  float pdf = 0.5f * 1.1283791670955126f * inv * __expf(-t * t);
+  return cdf + x * pdf;
+}
+
+struct TileCoord {
+  int m_blk, n_blk, split;
+};
+
+__device__ __forceinline__ TileCoord tile_coord(int tile, int num_m, int num_n) {
+  const int per_split = num_m * num_n;
+  TileCoord c;
+  c.split = tile / per_split;
+  int t = tile - c.split * per_split;
+  const int group_sz = GEMM_GROUP_M * num_n;
+  int g = t / group_sz;
+  int first_m = g * GEMM_GROUP_M;
+  int gm = min(GEMM_GROUP_M, num_m - first_m);
+  int r = t - g * group_sz;
+  c.m_blk = first_m + r % gm;
+  c.n_blk = r / gm;
+  return c;
+}
+
+template <int kCG>
+struct GemmCfg {
+  static constexpr int STAGES = kCG == 1 ? 4 : 6;
+  static constexpr int BNL = GEMM_BN / kCG;  // rows of B each CTA loads
+  static constexpr uint32_t A_BYTES = GEMM_BM_CTA * GEMM_BK * 2;
+  static constexpr uint32_t B_BYTES = BNL * GEMM_BK * 2;
+  static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
+};
+
+template <int kCG, bool kAMN, bool kBMN>
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<kCG>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr uint32_t A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCG == 2) ? cluster_ctarank() : 0u;
+  const int cluster_id = (kCG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const int num_clusters = (kCG == 2) ? (gridDim.x >> 1) : gridDim.x;
+  const int total_tiles = p.num_m * p.num_n * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], kCG);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4 * kCG);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<kCG>(tmem_slot, 512);
+  }
+  tc_fence_before();
+  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const TileCoord tc = tile_coord(tile, p.num_m, p.num_n);
+        const int m0 = tc.m_blk * (GEMM_BM_CTA * kCG) + static_cast<int>(cta_rank) * GEMM_BM_CTA;
+        const int n0 = tc.n_blk * GEMM_BN + static_cast<int>(cta_rank) * Cfg::BNL;
+        const int kb0 = tc.split * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* a_dst = sA + stage * A_BYTES;
+          uint8_t* b_dst = sB + stage * B_BYTES;
+          const int k0 = kb * GEMM_BK;
+          if constexpr (kCG == 1) {
+            mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
+            if constexpr (!kAMN) {
+              tma_load_2d(&tmA, &full[stage], a_dst, k0, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < GEMM_BM_CTA / 64; ++j) tma_load_2d(&tmA, &full[stage], a_dst + j * 8192, m0 + j * 64, k0);
+            }
+            if constexpr (!kBMN) {
+              tma_load_2d(&tmB, &full[stage], b_dst, k0, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < Cfg::BNL / 64; ++j) tma_load_2d(&tmB, &full[stage], b_dst + j * 8192, n0 + j * 64, k0);
+            }
+          } else {
+            if (cta_rank == 0) mbar_expect_tx(&full[stage], (A_BYTES + B_BYTES) * 2);
+            if constexpr (!kAMN) {
+              tma_load_2d_2sm(&tmA, &full[stage], a_dst, k0, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < GEMM_BM_CTA / 64; ++j)
+                tma_load_2d_2sm(&tmA, &full[stage], a_dst + j * 8192, m0 + j * 64, k0);
+            }
+            if constexpr (!kBMN) {
+              tma_load_2d_2sm(&tmB, &full[stage], b_dst, k0, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < Cfg::BNL / 64; ++j)
+                tma_load_2d_2sm(&tmB, &full[stage], b_dst + j * 8192, n0 + j * 64, k0);
+            }
+            if (cta_rank != 0) mbar_arrive_cluster(&full[stage], 0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM_CTA * kCG, GEMM_BN, kAMN, kBMN);
+      constexpr uint32_t A_LBO = kAMN ? GEMM_BK * 128 : 0;
+      constexpr uint32_t B_LBO = kBMN ? GEMM_BK * 128 : 0;
+      constexpr uint32_t A_KSTEP = kAMN ? 16 * 128 : 32;  // bytes per UMMA_K=16 step
+      constexpr uint32_t B_KSTEP = kBMN ? 16 * 128 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+        const TileCoord tc = tile_coord(tile, p.num_m, p.num_n);
+        const int kb0 = tc.split * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int acc_stage = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc_stage], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc_stage * GEMM_BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t a_desc = make_smem_desc_sw128(a_addr + k * A_KSTEP, A_LBO, 1024);
+            const uint64_t b_desc = make_smem_desc_sw128(b_addr + k * B_KSTEP, B_LBO, 1024);
+            umma_bf16_ss<kCG>(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          if constexpr (kCG == 1) umma_commit(&empty[stage]); else umma_commit_2sm(&empty[stage], 0x3);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if constexpr (kCG == 1) umma_commit(&tfull[acc_stage]); else umma_commit_2sm(&tfull[acc_stage], 0x3);
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+      const TileCoord tc = tile_coord(tile, p.num_m, p.num_n);
+      const int acc_stage = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const long long row = static_cast<long long>(tc.m_blk) * (GEMM_BM_CTA * kCG) + cta_rank * GEMM_BM_CTA + q * 32 + lane;
+      const int n0 = tc.n_blk * GEMM_BN;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tfull[acc_stage], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * GEMM_BN;
+#pragma unroll 1
+      for (int c = 0; c < GEMM_BN / 32; ++c) {
+        uint32_t r[32];
+        __syncwarp();  // re-converge after the lane-divergent `continue`s below: tcgen05.ld is .sync.aligned
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (!row_ok || col0 >= p.N) continue;
+        const bool full_chunk = p.vec_ok && (col0 + 32 <= p.N);
+        if (p.epi == EPI_PARTIAL) {
+          float* dst = p.partial + (static_cast<size_t>(tc.split) * p.M + row) * p.N + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<uint4*>(dst)[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          } else {
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __uint_as_float(r[j]);
+          }
+          continue;
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = rb(__uint_as_float(r[j]));
+        if (p.epi == EPI_RESID || p.epi == EPI_GELU_BWD || p.epi == EPI_RESID_DROPOUT) {
+          const __nv_bfloat16* src = p.aux_in + row * p.ld_aux_in + col0;
+          float a[32];
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u = reinterpret_cast<const uint4*>(src)[j];
+              a[8 * j + 0] = bf16_lo(u.x); a[8 * j + 1] = bf16_hi(u.x);
+              a[8 * j + 2] = bf16_lo(u.y); a[8 * j + 3] = bf16_hi(u.y);
+              a[8 * j + 4] = bf16_lo(u.z); a[8 * j + 5] = bf16_hi(u.z);
+              a[8 * j + 6] = bf16_lo(u.w); a[8 * j + 7] = bf16_hi(u.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = (col0 + j < p.N) ? __bfloat162float(src[j]) : 0.f;
+          }
+          if (p.epi == EPI_RESID) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = a[j] + v[j];
+          } else if (p.epi == EPI_GELU_BWD) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * gelu_grad_ref(a[j]);
+          } else {
+            // resid dropout: one Philox call per 4 consecutive columns, keyed by the flat element index
+            const float scale = 1.0f / (1.0f - p.drop_p);
+            const unsigned long long base = (static_cast<unsigned long long>(row) * p.N + col0) >> 2;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              uint4 rnd = philox4x32(p.seed, base + j4, p.offset);
+              const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float u01 = (rr[e] >> 8) * (1.0f / 16777216.0f);
+                float d = (u01 >= p.drop_p) ? rb(v[4 * j4 + e] * scale) : 0.f;
+                v[4 * j4 + e] = a[4 * j4 + e] + d;
+              }
+            }
+          }
+        } else if (p.epi == EPI_GELU) {
+          __nv_bfloat16* udst = p.aux_out + row * p.ld_aux_out + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              reinterpret_cast<uint4*>(udst)[j] =
+                  make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                             pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          } else {
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j) udst[j] = __float2bfloat16_rn(v[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_ref(v[j], p.gelu_mode);
+        }
+        __nv_bfloat16* dst = p.D + row * p.ldd + col0;
+        if (full_chunk) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            reinterpret_cast<uint4*>(dst)[j] =
+                make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        } else {
+          for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+        }
+      }
+      // release this accumulator stage back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCG == 1) mbar_arrive(&tempty[acc_stage]); else mbar_arrive_cluster(&tempty[acc_stage], 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<kCG>(tmem_base, 512);
+  }
+}
+
+// out[m,n] = rb( (accumulate ? float(out[m,n]) : 0) + float(rb(sum_s partial[s][m][n])) )
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ out, long long ldd,
+                                     int M, int N, int splits, int accumulate) {
+  const long long total4 = static_cast<long long>(M) * N / 4;
+  const long long stride = static_cast<long long>(M) * N;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 acc = reinterpret_cast<const float4*>(partial)[i];
+    for (int s = 1; s < splits; ++s) {
+      float4 t = reinterpret_cast<const float4*>(partial + s * stride)[i];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    const long long e = i * 4;
+    const long long m = e / N;
+    const int n = static_cast<int>(e - m * N);
+    __nv_bfloat16* dst = out + m * ldd + n;
+    float o[4] = {rb(acc.x), rb(acc.y), rb(acc.z), rb(acc.w)};
+    if (accumulate) {
+      uint2 old = *reinterpret_cast<const uint2*>(dst);
+      o[0] += bf16_lo(old.x); o[1] += bf16_hi(old.x); o[2] += bf16_lo(old.y); o[3] += bf16_hi(old.y);
+    }
+    *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+  }
+}
+
+template <int kCG, bool kAMN, bool kBMN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<kCG>;
+  auto kern = gemm_bf16_kernel<kCG, kAMN, kBMN>;
+  static bool attr_set = false;  // benign race: idempotent
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(gemm smem=%u): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return OBT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int total_tiles = p.num_m * p.num_n * p.splits;
+  const int max_clusters = sm_count() / kCG;
+  const int clusters = total_tiles < max_clusters ? total_tiles : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * kCG);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  if (e != cudaSuccess) {
+    set_last_error("gemm launch: %s", cudaGetErrorString(e));
+    return OBT_ERR_CUDA;
+  }
+  return OBT_OK;
+}
+
+static int g_force_cta_group = 0;  // 0 = auto, 1 or 2 = forced (tests / ablations)
+
+}  // namespace obt
+
+using namespace obt;
+
+extern "C" void obt_gemm_set_cta_group(int cg) { obt::g_force_cta_group = cg; }
+
+// Number of fp32 elements of workspace obt_gemm_bf16 wants for this problem when split-K is allowed.
+extern "C" long long obt_gemm_workspace_elems(long long M, long long N, long long K) {
+  (void)K;
+  // at most 8 splits
+  return 8 * M * N;
+}
+
+extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M, long long N, long long K,
+                             long long lda, long long ldb, long long ldd, int a_mn_major, int b_mn_major,
+                             int epilogue, const void* aux_in, long long ld_aux_in, void* aux_out,
+                             long long ld_aux_out, int gelu_mode, float drop_p, unsigned long long seed,
+                             unsigned long long offset, void* workspace, long long workspace_elems,
+                             cudaStream_t stream) {
+  OBT_REQUIRE(A && B && D, "obt_gemm_bf16: null operand");
+  OBT_REQUIRE(M > 0 && N > 0 && K > 0, "obt_gemm_bf16: empty problem M=%lld N=%lld K=%lld", M, N, K);
+  OBT_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "obt_gemm_bf16: dims exceed int32");
+  OBT_REQUIRE(epilogue >= EPI_PLAIN && epilogue <= EPI_RESID_DROPOUT && epilogue != EPI_PARTIAL,
+              "obt_gemm_bf16: bad epilogue %d", epilogue);
+  if (epilogue == EPI_RESID || epilogue == EPI_GELU_BWD || epilogue == EPI_RESID_DROPOUT)
+    OBT_REQUIRE(aux_in != nullptr, "obt_gemm_bf16: epilogue %d needs aux_in", epilogue);
+  if (epilogue == EPI_GELU) OBT_REQUIRE(aux_out != nullptr, "obt_gemm_bf16: GELU epilogue needs aux_out");
+
+  int cg = g_force_cta_group;
+  if (cg == 0) cg = (M > 128) ? 2 : 1;
+  const int bm = GEMM_BM_CTA * cg;
+
+  GemmParams p = {};
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.K = static_cast<int>(K);
+  p.num_m = static_cast<int>((M + bm - 1) / bm);
+  p.num_n = static_cast<int>((N + GEMM_BN - 1) / GEMM_BN);
+  p.num_kb = static_cast<int>((K + GEMM_BK - 1) / GEMM_BK);
+  p.epi = epilogue;
+  p.gelu_mode = gelu_mode;
+  p.D = static_cast<__nv_bfloat16*>(D);
+  p.ldd = ldd;
+  p.aux_in = static_cast<const __nv_bfloat16*>(aux_in);
+  p.ld_aux_in = ld_aux_in;
+  p.aux_out = static_cast<__nv_bfloat16*>(aux_out);
+  p.ld_aux_out = ld_aux_out;
+  p.drop_p = drop_p;
+  p.seed = seed;
+  p.offset = offset;
+  auto aligned16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+  p.vec_ok = (N % 8 == 0) && (ldd % 8 == 0) && aligned16(D) &&
+             (aux_in == nullptr || (ld_aux_in % 8 == 0 && aligned16(aux_in))) &&
+             (aux_out == nullptr || (ld_aux_out % 8 == 0 && aligned16(aux_out)));
+
+  // split-K when the output tile grid cannot fill the machine and the reduction is long (wgrad shapes).
+  p.splits = 1;
+  const int tiles = p.num_m * p.num_n;
+  const int slots = sm_count() / cg;
+  const bool splittable = (epilogue == EPI_PLAIN || (epilogue == EPI_RESID && aux_in == D && ld_aux_in == ldd)) &&
+                          workspace != nullptr && (M * N) % 4 == 0 && (N % 4 == 0) && (ldd % 4 == 0);
+  if (splittable && tiles * 2 <= slots && p.num_kb >= 16) {
+    int s = slots / tiles;
+    if (s > 8) s = 8;
+    while (s > 1 && (p.num_kb / s) < 4) --s;
+    while (s > 1 && static_cast<long long>(s) * M * N > workspace_elems) --s;
+    p.splits = s;
+  }
+  p.kb_per_split = (p.num_kb + p.splits - 1) / p.splits;
+  // all splits must be non-empty
+  while (p.splits > 1 && (p.splits - 1) * p.kb_per_split >= p.num_kb) {
+    --p.splits;
+    p.kb_per_split = (p.num_kb + p.splits - 1) / p.splits;
+  }
+  int final_epi = epilogue;
+  if (p.splits > 1) {
+    p.partial = static_cast<float*>(workspace);
+    p.epi = EPI_PARTIAL;
+  }
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  const int bnl = GEMM_BN / cg;
+  if (!a_mn_major) {
+    OBT_REQUIRE(lda % 8 == 0, "obt_gemm_bf16: lda=%lld must be a multiple of 8 elements", lda);
+    rc = get_tensor_map_2d(&tmA, A, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda), 64,
+                           GEMM_BM_CTA);
+  } else {
+    OBT_REQUIRE(lda % 8 == 0, "obt_gemm_bf16: lda=%lld must be a multiple of 8 elements", lda);
+    rc = get_tensor_map_2d(&tmA, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), 64,
+                           64);
+  }
+  if (rc != OBT_OK) return rc;
+  OBT_REQUIRE(ldb % 8 == 0, "obt_gemm_bf16: ldb=%lld must be a multiple of 8 elements", ldb);
+  if (!b_mn_major) {
+    rc = get_tensor_map_2d(&tmB, B, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldb), 64,
+                           static_cast<uint32_t>(bnl));
+  } else {
+    rc = get_tensor_map_2d(&tmB, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), 64,
+                           64);
+  }
+  if (rc != OBT_OK) return rc;
+
+#define OBT_LAUNCH(CG, AM, BM_)                                                  \
+  if (cg == CG && (a_mn_major != 0) == AM && (b_mn_major != 0) == BM_) {          \
+    rc = launch_gemm<CG, AM, BM_>(tmA, tmB, p, stream);                          \
+  } else
+  OBT_LAUNCH(1, false, false)
+  OBT_LAUNCH(1, false, true)
+  OBT_LAUNCH(1, true, false)
+  OBT_LAUNCH(1, true, true)
+  OBT_LAUNCH(2, false, false)
+  OBT_LAUNCH(2, false, true)
+  OBT_LAUNCH(2, true, false)
+  OBT_LAUNCH(2, true, true) {
+    set_last_error("obt_gemm_bf16: no kernel for cta_group=%d", cg);
+    rc = OBT_ERR_UNSUPPORTED;
+  }
+#undef OBT_LAUNCH
+  if (rc != OBT_OK) return rc;
+
+  if (p.splits > 1) {
+    const long long total4 = M * N / 4;
+    int blocks = static_cast<int>((total4 + 255) / 256);
+    const int cap = sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, p.D, ldd, p.M, p.N, p.splits,
+                                                    final_epi == EPI_RESID ? 1 : 0);
+    return check_launch("splitk_reduce");
+  }
+  return OBT_OK;
+}

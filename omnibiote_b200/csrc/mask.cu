@@ -1,0 +1,184 @@
+// Attention-mask producers / compressors for the hot path's input contract.
+//
+//  * obt_doc_mask_intervals : per-token visible key interval [lo,hi) straight from token ids, reproducing the
+//    reference builder `create_attention_mask` (training/train_encoder.py:25-57) including its quirks: for every
+//    batch row except the one handled first by the `if` branch (row 0), the first two documents are merged; with
+//    padding=False an EOS is virtually appended; with padding=True a row without any EOS attends everywhere and
+//    tokens after the last EOS are fully masked (finite -1e9 everywhere => uniform attention).
+//  * obt_pad_mask_intervals : `pad_attn` of evals/gue.py:15-21 (rows/cols after first_pad+1 masked).
+//  * obt_mask_from_intervals: materialises the dense additive bf16 (B,T,T) tensor {0, -1e9} for drop-in callers.
+//  * obt_mask_compress      : the inverse: dense additive mask -> intervals + a flag telling whether the mask is
+//    exactly interval-structured with values {0, bf16(-1e9)} (otherwise the dense path must be used).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace obt {
+
+__global__ void doc_mask_intervals_kernel(const long long* __restrict__ ids, int* __restrict__ lo, int* __restrict__ hi,
+                                          int T, long long eos, int padding) {
+  extern __shared__ int s_eos[];  // positions of EOS tokens in this row (at most T+1)
+  __shared__ int s_n;
+  const int b = blockIdx.x;
+  const long long* row = ids + static_cast<long long>(b) * T;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int t = 0; t < T; ++t)
+      if (row[t] == eos) s_eos[n++] = t;
+    if (!padding) s_eos[n++] = T;  // virtual EOS appended at position T (train_encoder.py:33-37)
+    s_n = n;
+  }
+  __syncthreads();
+  const int n = s_n;
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    int l = 0, h = 0;
+    if (n == 0) {
+      l = 0; h = T;  // no EOS in the row: everything visible (train_encoder.py:53-55)
+    } else {
+      // k = index of the first EOS at or after i
+      int a = 0, c = n;
+      while (a < c) {
+        int m = (a + c) >> 1;
+        if (s_eos[m] >= i) c = m; else a = m + 1;
+      }
+      const int k = a;
+      if (k < n) {
+        l = (k == 0) ? 0 : s_eos[k - 1] + 1;
+        h = min(s_eos[k] + 1, T);
+        if (b > 0 && k <= 1) {
+          // quirk: rows entered through the `else` branch never advance prev_index on their first EOS, so the
+          // block of the second EOS starts at 0 again: documents 0 and 1 are merged (train_encoder.py:44-51)
+          l = 0;
+          h = min(s_eos[n > 1 ? 1 : 0] + 1, T);
+        }
+      }  // else: after the last EOS -> fully masked row (l == h == 0)
+    }
+    lo[static_cast<long long>(b) * T + i] = l;
+    hi[static_cast<long long>(b) * T + i] = h;
+  }
+}
+
+__global__ void pad_mask_intervals_kernel(const long long* __restrict__ ids, int* __restrict__ lo, int* __restrict__ hi,
+                                          int T, long long pad) {
+  __shared__ int s_first;
+  const int b = blockIdx.x;
+  const long long* row = ids + static_cast<long long>(b) * T;
+  if (threadIdx.x == 0) s_first = T;
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x)
+    if (row[t] == pad) atomicMin(&s_first, t);
+  __syncthreads();
+  // gue.py:18-19: rows and columns from first_pad + 1 on are masked; the first PAD itself stays attended.
+  const int vis = min(T, s_first + 1);
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    const bool live = i < vis;
+    lo[static_cast<long long>(b) * T + i] = 0;
+    hi[static_cast<long long>(b) * T + i] = live ? vis : 0;
+  }
+}
+
+// mask[b,i,j] = (lo <= j < hi) ? 0 : -1e9 (bf16: 0xCE6E); 8 elements per thread
+__global__ void mask_from_intervals_kernel(const int* __restrict__ lo, const int* __restrict__ hi,
+                                           __nv_bfloat16* __restrict__ mask, long long rows, int T) {
+  const int chunks = T / 8;
+  const long long total = rows * chunks;
+  const uint32_t NEG = 0xCE6Eu;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = e / chunks;
+    const int j0 = static_cast<int>(e - r * chunks) * 8;
+    const int l = lo[r], h = hi[r];
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = j0 + 2 * k;
+      const uint32_t a = (j >= l && j < h) ? 0u : NEG;
+      const uint32_t c = (j + 1 >= l && j + 1 < h) ? 0u : NEG;
+      w[k] = a | (c << 16);
+    }
+    reinterpret_cast<uint4*>(mask + r * T)[j0 / 8] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// One warp per (b,i) row of a dense additive bf16 mask: find [lo,hi) of zeros and verify the structure.
+__global__ void mask_compress_kernel(const __nv_bfloat16* __restrict__ mask, long long msb, long long msq,
+                                     int* __restrict__ lo, int* __restrict__ hi, int* __restrict__ not_interval, int B,
+                                     int T) {
+  const int warps = blockDim.x >> 5;
+  const long long r = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5);
+  if (r >= static_cast<long long>(B) * T) return;
+  const int lane = threadIdx.x & 31;
+  const int b = static_cast<int>(r / T), i = static_cast<int>(r % T);
+  const unsigned short* row = reinterpret_cast<const unsigned short*>(mask + b * msb + i * msq);
+  int first = T, last = -1, zeros = 0, bad = 0;
+  for (int j = lane; j < T; j += 32) {
+    const unsigned short v = row[j];
+    if (v == 0 || v == 0x8000u) {
+      first = min(first, j);
+      last = max(last, j);
+      ++zeros;
+    } else if (v != 0xCE6Eu) {
+      bad = 1;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if (lane == 0) {
+    if (zeros == 0) {
+      lo[r] = 0; hi[r] = 0;
+    } else {
+      lo[r] = first; hi[r] = last + 1;
+      if (zeros != last + 1 - first) bad = 1;
+    }
+    if (bad) atomicExch(not_interval, 1);
+  }
+}
+
+}  // namespace obt
+
+using namespace obt;
+
+extern "C" int obt_doc_mask_intervals(const long long* ids, int* lo, int* hi, int B, int T, long long eos_token,
+                                      int padding, cudaStream_t stream) {
+  OBT_REQUIRE(ids && lo && hi, "obt_doc_mask_intervals: null pointer");
+  OBT_REQUIRE(B > 0 && T > 0 && T <= 32768, "obt_doc_mask_intervals: bad shape B=%d T=%d", B, T);
+  doc_mask_intervals_kernel<<<B, 256, (T + 1) * sizeof(int), stream>>>(ids, lo, hi, T, eos_token, padding);
+  return check_launch("doc_mask_intervals");
+}
+
+extern "C" int obt_pad_mask_intervals(const long long* ids, int* lo, int* hi, int B, int T, long long pad_token,
+                                      cudaStream_t stream) {
+  OBT_REQUIRE(ids && lo && hi, "obt_pad_mask_intervals: null pointer");
+  OBT_REQUIRE(B > 0 && T > 0, "obt_pad_mask_intervals: bad shape");
+  pad_mask_intervals_kernel<<<B, 256, 0, stream>>>(ids, lo, hi, T, pad_token);
+  return check_launch("pad_mask_intervals");
+}
+
+extern "C" int obt_mask_from_intervals(const int* lo, const int* hi, void* mask, int B, int T, cudaStream_t stream) {
+  OBT_REQUIRE(lo && hi && mask, "obt_mask_from_intervals: null pointer");
+  OBT_REQUIRE(T % 8 == 0, "obt_mask_from_intervals: T=%d must be a multiple of 8", T);
+  const long long rows = static_cast<long long>(B) * T;
+  const long long total = rows * (T / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  mask_from_intervals_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(lo, hi, static_cast<__nv_bfloat16*>(mask),
+                                                                              rows, T);
+  return check_launch("mask_from_intervals");
+}
+
+// mask: additive bf16 (b, i, j) with strides (msb, msq, 1). not_interval (device int, pre-zeroed) is set to 1 when any
+// row is not {0,-1e9}-valued with a single contiguous run of zeros.
+extern "C" int obt_mask_compress(const void* mask, long long msb, long long msq, int* lo, int* hi, int* not_interval,
+                                 int B, int T, cudaStream_t stream) {
+  OBT_REQUIRE(mask && lo && hi && not_interval, "obt_mask_compress: null pointer");
+  const long long rows = static_cast<long long>(B) * T;
+  const int warps = 8;
+  mask_compress_kernel<<<static_cast<unsigned>((rows + warps - 1) / warps), warps * 32, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(mask), msb, msq, lo, hi, not_interval, B, T);
+  return check_launch("mask_compress");
+}

@@ -1,0 +1,238 @@
+"""Autograd glue for the encoder hot path: each ``torch.autograd.Function`` below owns one fused forward/backward
+schedule of C-ABI kernel calls (``ops.py``). Torch only records the graph between them, so the evals'
+``loss.backward()`` and stock optimizers keep working on the drop-in module (``model.py``).
+
+Reference arithmetic followed (rounding points as in SURVEY Appendix D):
+  Block            training/model.py:170-181  (pre-LN residual block; SelfAttention :98-152; MLP :162-168)
+  embedding        training/model.py:241-242
+  ln_f / MuReadout training/model.py:248-254 + mup MuReadout.forward
+  MLM loss         training/train_encoder.py:301-305
+"""
+from __future__ import annotations
+
+import contextlib
+
+import torch
+
+from . import ops
+
+# When enabled (by the trainer), weight gradients are accumulated by the GEMM epilogue straight into the existing
+# ``param.grad`` buffer (bf16 ``+=`` like autograd's accumulation) and autograd receives ``None`` for them.
+_DIRECT_GRAD = False
+
+
+@contextlib.contextmanager
+def direct_grad_accumulation(enabled: bool = True):
+    global _DIRECT_GRAD
+    prev, _DIRECT_GRAD = _DIRECT_GRAD, enabled
+    try:
+        yield
+    finally:
+        _DIRECT_GRAD = prev
+
+
+def _wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, param):
+    """dW[N,K] = dy[M,N]^T @ x[M,K] (both operands MN-major for the tensor cores, no transposes materialised)."""
+    if _DIRECT_GRAD and param is not None and param.grad is not None:
+        ops.gemm(dy2d, x2d, out=param.grad, a_mn=True, b_mn=True, epilogue=ops.EPI_RESID, aux_in=param.grad)
+        return None
+    return ops.gemm(dy2d, x2d, a_mn=True, b_mn=True)
+
+
+def _vec_grad(g: torch.Tensor, param):
+    if _DIRECT_GRAD and param is not None and param.grad is not None:
+        return None  # already accumulated in place by the kernel
+    return g
+
+
+class EmbedFunction(torch.autograd.Function):
+    """x0 = dropout(wte[idx])  (model.py:241-242). Output [M, C]."""
+
+    @staticmethod
+    def forward(ctx, idx, wte, p_drop, training):
+        p = float(p_drop) if training else 0.0
+        seed = off = 0
+        if p > 0.0:
+            seed, off = ops.philox_args(wte.device, 4)
+        out = ops.embed_fwd(idx, wte, p, seed, off)
+        ctx.save_for_backward(idx)
+        ctx.meta = (p, seed, off, wte.shape)
+        ctx.param = wte
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        p, seed, off, shape = ctx.meta
+        w = ctx.param
+        dout = dout.contiguous()
+        if _DIRECT_GRAD and w.grad is not None:
+            ops.embed_bwd(idx, dout, w.grad, True, p, seed, off)
+            return None, None, None, None
+        dw = torch.empty(shape, dtype=torch.bfloat16, device=dout.device)
+        ops.embed_bwd(idx, dout, dw, False, p, seed, off)
+        return None, dw, None, None
+
+
+class BlockFunction(torch.autograd.Function):
+    """x -> x + attn(ln_1(x)) -> (+ mlp(ln_2(.)))  (model.py:170-181). x is [M, C] with M = B*T."""
+
+    @staticmethod
+    def forward(ctx, x, g1, w_qkv, w_o, g2, w_fc, w_pr, cos_tab, sin_tab, mask, B, T, H, p_drop, training):
+        M, C = x.shape
+        d = C // H
+        p = float(p_drop) if training else 0.0
+        dev = x.device
+        seeds = [(0, 0)] * 3
+        if p > 0.0:
+            seeds = [ops.philox_args(dev, 4) for _ in range(3)]  # attn P, attn resid, mlp resid
+        scale = 8.0 / C  # model.py:119,135: 8 / n_embd, independent of n_head
+
+        h1, _, mean1, rstd1 = ops.layernorm_fwd(x, g1)
+        qkv = ops.gemm(h1, w_qkv)
+        ops.rope_(qkv, cos_tab, sin_tab, T, C, d)
+        y, lse = ops.attention_fwd(qkv, B, T, H, d, scale, mask, p, *seeds[0])
+        if p > 0.0:
+            x1 = ops.gemm(y, w_o, epilogue=ops.EPI_RESID_DROPOUT, aux_in=x, drop_p=p, seed=seeds[1][0], offset=seeds[1][1])
+        else:
+            x1 = ops.gemm(y, w_o, epilogue=ops.EPI_RESID, aux_in=x)
+        h2, _, mean2, rstd2 = ops.layernorm_fwd(x1, g2)
+        u = torch.empty((M, w_fc.shape[0]), dtype=torch.bfloat16, device=dev)
+        g = ops.gemm(h2, w_fc, epilogue=ops.EPI_GELU, aux_out=u)
+        if p > 0.0:
+            x2 = ops.gemm(g, w_pr, epilogue=ops.EPI_RESID_DROPOUT, aux_in=x1, drop_p=p, seed=seeds[2][0], offset=seeds[2][1])
+        else:
+            x2 = ops.gemm(g, w_pr, epilogue=ops.EPI_RESID, aux_in=x1)
+
+        ctx.save_for_backward(x, g1, w_qkv, w_o, g2, w_fc, w_pr, cos_tab, sin_tab, mean1, rstd1, h1, qkv, y, lse, x1,
+                              mean2, rstd2, h2, u, g)
+        ctx.mask = mask
+        ctx.meta = (B, T, H, d, p, seeds, scale)
+        ctx.params = (g1, w_qkv, w_o, g2, w_fc, w_pr)
+        return x2
+
+    @staticmethod
+    def backward(ctx, dx2):
+        (x, g1, w_qkv, w_o, g2, w_fc, w_pr, cos_tab, sin_tab, mean1, rstd1, h1, qkv, y, lse, x1, mean2, rstd2, h2, u,
+         g) = ctx.saved_tensors
+        B, T, H, d, p, seeds, scale = ctx.meta
+        pg1, pqkv, po, pg2, pfc, ppr = ctx.params
+        C = x.shape[1]
+        dx2 = dx2.contiguous()
+        direct = _DIRECT_GRAD
+
+        # ---- MLP branch: x2 = x1 + dropout(g @ Wpr^T)
+        d_dd = ops.dropout(dx2, p, *seeds[2]) if p > 0.0 else dx2
+        dw_pr = _wgrad(d_dd, g, ppr)
+        du = ops.gemm(d_dd, w_pr, b_mn=True, epilogue=ops.EPI_GELU_BWD, aux_in=u)
+        dw_fc = _wgrad(du, h2, pfc)
+        dh2 = ops.gemm(du, w_fc, b_mn=True)
+        acc2 = direct and pg2.grad is not None
+        dx1, dg2 = ops.layernorm_bwd(dh2, x1, g2, mean2, rstd2, dres=dx2, dgamma=pg2.grad if acc2 else None,
+                                     accumulate_dgamma=acc2)
+
+        # ---- attention branch: x1 = x + dropout(y @ Wo^T)
+        d_a = ops.dropout(dx1, p, *seeds[1]) if p > 0.0 else dx1
+        dw_o = _wgrad(d_a, y, po)
+        dy = ops.gemm(d_a, w_o, b_mn=True)
+        dqkv = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, ctx.mask, p, *seeds[0])
+        ops.rope_(dqkv, cos_tab, sin_tab, T, C, d, inverse=True)
+        dw_qkv = _wgrad(dqkv, h1, pqkv)
+        dh1 = ops.gemm(dqkv, w_qkv, b_mn=True)
+        acc1 = direct and pg1.grad is not None
+        dx, dg1 = ops.layernorm_bwd(dh1, x, g1, mean1, rstd1, dres=dx1, dgamma=pg1.grad if acc1 else None,
+                                    accumulate_dgamma=acc1)
+        return (dx, None if acc1 else dg1, dw_qkv, dw_o, None if acc2 else dg2, dw_fc, dw_pr, None, None, None, None,
+                None, None, None, None)
+
+
+class LayerNormFunction(torch.autograd.Function):
+    """F.layer_norm(x, (C,), weight, None, 1e-5) on [M, C]  (model.py:63-72)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma):
+        y, _, mean, rstd = ops.layernorm_fwd(x, gamma)
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.param = gamma
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        pg = ctx.param
+        acc = _DIRECT_GRAD and pg.grad is not None
+        dx, dg = ops.layernorm_bwd(dy.contiguous(), x, gamma, mean, rstd, dgamma=pg.grad if acc else None,
+                                   accumulate_dgamma=acc)
+        return dx, (None if acc else dg)
+
+
+class ReadoutFunction(torch.autograd.Function):
+    """MuReadout: logits = Linear(output_mult * x / width_mult)  (mup MuReadout.forward; model.py:208,253)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, div):
+        z = ops.scale_div(x, div)
+        logits = ops.gemm(z, weight)
+        ctx.save_for_backward(z, weight)
+        ctx.div = div
+        ctx.param = weight
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        z, weight = ctx.saved_tensors
+        dlogits = dlogits.contiguous()
+        dw = _wgrad(dlogits, z, ctx.param)
+        dz = ops.gemm(dlogits, weight, b_mn=True)
+        return ops.scale_div(dz, ctx.div), dw, None
+
+
+class HeadLossFunction(torch.autograd.Function):
+    """ln_f -> MuReadout -> masked-LM cross-entropy in one schedule (model.py:248-254 + train_encoder.py:301-305).
+
+    The logits (M x V bf16) are materialised once; the CE backward overwrites them in place with d loss / d logits
+    during the forward (rows outside the MLM mask are exact zeros, as in the reference), and the two head GEMMs of
+    the backward consume that buffer. Returns the bf16-rounded scalar loss of the reference.
+    """
+
+    @staticmethod
+    def forward(ctx, x, gamma, weight, div, targets, loss_mask, n_acc):
+        emb, z, mean, rstd = ops.layernorm_fwd(x, gamma, readout_div=div)
+        del emb
+        logits = ops.gemm(z, weight)
+        scalars, lse, tok, row_mask, tgt = ops.ce_fwd(logits, targets, loss_mask, n_acc)
+        ops.ce_bwd_(logits, tgt, row_mask, lse, scalars, 1.0)
+        ctx.save_for_backward(x, gamma, weight, mean, rstd, z, logits)
+        ctx.div = div
+        ctx.params = (gamma, weight)
+        ctx.mark_non_differentiable(scalars)
+        loss = scalars[0].to(torch.bfloat16)
+        return loss, scalars
+
+    @staticmethod
+    def backward(ctx, dloss, _dscalars):
+        x, gamma, weight, mean, rstd, z, dlogits = ctx.saved_tensors
+        pg, pw = ctx.params
+        # `loss.backward()` feeds exactly 1; any other upstream factor is folded in afterwards on the small tensors.
+        dw = _wgrad(dlogits, z, pw)
+        dz = ops.gemm(dlogits, weight, b_mn=True)
+        acc = _DIRECT_GRAD and pg.grad is not None
+        dx, dg = ops.layernorm_bwd(dz, x, gamma, mean, rstd, dgamma=pg.grad if acc else None, accumulate_dgamma=acc,
+                                   dy_div=ctx.div)
+        return dx, (None if acc else dg), dw, None, None, None, None
+
+
+class PoolFunction(torch.autograd.Function):
+    """encode() pooling over the token axis: mean / max  (model.py:269-278)."""
+
+    @staticmethod
+    def forward(ctx, emb, mode):
+        out = ops.pool(emb, mode)
+        ctx.save_for_backward(emb, out)
+        ctx.mode = mode
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        emb, out = ctx.saved_tensors
+        return ops.pool_bwd(emb, out, dout, ctx.mode), None

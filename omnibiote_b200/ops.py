@@ -1,0 +1,351 @@
+"""Thin tensor-level wrappers over the C ABI (``include/omnibiote_b200.h``).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every computation below is a call into
+``libomnibiote_b200.so``. There is no CPU or eager fallback: non-CUDA / non-bf16 inputs raise.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+EPI_PLAIN, EPI_RESID, EPI_GELU, EPI_GELU_BWD, EPI_RESID_DROPOUT = 0, 1, 2, 3, 5
+
+# gelu_mode 0: one rounding (TorchScript-fused execution on CUDA); 1: a bf16 rounding per primitive (eager CPU run of
+# the same expression, which is what the CPU oracle does). See SURVEY Appendix A.2.
+GELU_MODE = 0
+
+_workspaces: dict = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.bfloat16) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"omnibiote_b200: {name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"omnibiote_b200: {name} must be {dtype}, got {t.dtype}")
+
+
+def workspace(key: str, numel: int, dtype, device, zero: bool = False) -> torch.Tensor:
+    """Cached scratch buffer (grown on demand). ``zero`` buffers are zero-filled when (re)allocated only."""
+    k = (key, dtype, device)
+    buf = _workspaces.get(k)
+    if buf is None or buf.numel() < numel:
+        buf = torch.zeros(numel, dtype=dtype, device=device) if zero else torch.empty(numel, dtype=dtype, device=device)
+        _workspaces[k] = buf
+    return buf
+
+
+def philox_args(device, increment: int = 4):
+    """Reserve a slice of the device's default Philox stream (so torch.manual_seed and checkpoint RNG replay work)."""
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    seed = gen.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    off = gen.get_offset()
+    gen.set_offset(off + increment)
+    return seed, off
+
+
+def _mat(t: torch.Tensor, name: str):
+    """2-D view with unit inner stride -> (tensor, leading dimension)."""
+    _req(t, name)
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError(f"omnibiote_b200: {name} must be 2-D with unit inner stride, got {tuple(t.shape)} / {t.stride()}")
+    return t, t.stride(0)
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a_mn: bool = False, b_mn: bool = False,
+         epilogue: int = EPI_PLAIN, aux_in: torch.Tensor | None = None, aux_out: torch.Tensor | None = None,
+         drop_p: float = 0.0, seed: int = 0, offset: int = 0, allow_splitk: bool = True) -> torch.Tensor:
+    """out[M,N] = epilogue(op(a) @ op(b)^T).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn)."""
+    a, lda = _mat(a, "gemm A")
+    b, ldb = _mat(b, "gemm B")
+    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else b.shape
+    if K != Kb:
+        raise RuntimeError(f"omnibiote_b200: gemm K mismatch {K} vs {Kb}")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    out, ldd = _mat(out, "gemm D")
+    if tuple(out.shape) != (M, N):
+        raise RuntimeError(f"omnibiote_b200: gemm D shape {tuple(out.shape)} != {(M, N)}")
+    ld_ai = ld_ao = 0
+    if aux_in is not None:
+        aux_in, ld_ai = _mat(aux_in, "gemm aux_in")
+    if aux_out is not None:
+        aux_out, ld_ao = _mat(aux_out, "gemm aux_out")
+    ws, ws_elems = None, 0
+    if allow_splitk and K >= 1024 and M * N <= 8 * 1024 * 1024:
+        ws_elems = 8 * M * N
+        ws = workspace("splitk", ws_elems, torch.float32, a.device)
+    lib = _lib.load()
+    rc = lib.obt_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldd, int(a_mn), int(b_mn),
+                           epilogue, _ptr(aux_in), ld_ai, _ptr(aux_out), ld_ao, GELU_MODE, float(drop_p), seed, offset,
+                           _ptr(ws), ws_elems, _stream())
+    _lib.check(rc, "obt_gemm_bf16")
+    return out
+
+
+def embed_fwd(idx: torch.Tensor, wte: torch.Tensor, drop_p: float = 0.0, seed: int = 0, offset: int = 0) -> torch.Tensor:
+    _req(wte, "wte")
+    _req(idx, "idx", torch.int64)
+    idx = idx.contiguous()
+    V, C = wte.shape
+    M = idx.numel()
+    out = torch.empty((M, C), dtype=torch.bfloat16, device=wte.device)
+    err = workspace("embed_err", 1, torch.int32, wte.device, zero=True)
+    rc = _lib.load().obt_embed_fwd(idx.data_ptr(), wte.data_ptr(), out.data_ptr(), M, C, V, float(drop_p), seed, offset,
+                                   err.data_ptr(), _stream())
+    _lib.check(rc, "obt_embed_fwd")
+    return out
+
+
+def embed_bwd(idx: torch.Tensor, dout: torch.Tensor, dwte: torch.Tensor, accumulate: bool, drop_p: float = 0.0,
+              seed: int = 0, offset: int = 0) -> None:
+    _req(dout, "dout")
+    _req(dwte, "dwte")
+    idx = idx.contiguous()
+    V, C = dwte.shape
+    M = idx.numel()
+    scratch = workspace("embed_scratch", V * C, torch.float32, dwte.device, zero=True)
+    touched = workspace("embed_touched", V, torch.int32, dwte.device, zero=True)
+    rc = _lib.load().obt_embed_bwd(idx.data_ptr(), dout.data_ptr(), dwte.data_ptr(), scratch.data_ptr(),
+                                   touched.data_ptr(), M, C, V, int(accumulate), float(drop_p), seed, offset, _stream())
+    _lib.check(rc, "obt_embed_bwd")
+
+
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-5, readout_div: float | None = None):
+    """Returns (y, z, mean, rstd); z = rb(y / readout_div) when readout_div is given (MuReadout input scaling)."""
+    _req(x, "ln x")
+    _req(gamma, "ln weight")
+    M, C = x.shape
+    y = torch.empty_like(x)
+    z = torch.empty_like(x) if readout_div is not None else None
+    mean = torch.empty(M, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+    rc = _lib.load().obt_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), y.data_ptr(), _ptr(z), mean.data_ptr(),
+                                       rstd.data_ptr(), M, C, eps, float(readout_div or 1.0), _stream())
+    _lib.check(rc, "obt_layernorm_fwd")
+    return y, z, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, dgamma=None, accumulate_dgamma=False, dy_div: float = 1.0):
+    """Returns (dx, dgamma). dx = rb(dres + rb(ln_bwd(rb(dy / dy_div))))."""
+    _req(dy, "ln dy")
+    M, C = x.shape
+    lib = _lib.load()
+    dx = torch.empty_like(x)
+    if dgamma is None:
+        dgamma = torch.empty(C, dtype=torch.bfloat16, device=x.device)
+        accumulate_dgamma = False
+    ws = workspace("ln_bwd", lib.obt_layernorm_bwd_workspace_rows() * C, torch.float32, x.device)
+    rc = lib.obt_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                               _ptr(dres), dx.data_ptr(), dgamma.data_ptr(), int(accumulate_dgamma), ws.data_ptr(), M, C,
+                               float(dy_div), _stream())
+    _lib.check(rc, "obt_layernorm_bwd")
+    return dx, dgamma
+
+
+def rope_(qkv: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torch.Tensor | None, T: int, C: int, head_dim: int,
+          inverse: bool = False) -> torch.Tensor:
+    """In-place rotary / cosine-scale on the q and k column ranges of qkv [M, 3C]."""
+    qkv, ld = _mat(qkv, "qkv")
+    _req(cos_tab, "cos table", torch.float32)
+    if cos_tab.shape[0] < T:
+        raise RuntimeError("omnibiote_b200: rotary table shorter than the sequence")
+    rc = _lib.load().obt_rope(qkv.data_ptr(), cos_tab.data_ptr(), _ptr(sin_tab), qkv.shape[0], T, C, head_dim, ld,
+                              int(inverse), _stream())
+    _lib.check(rc, "obt_rope")
+    return qkv
+
+
+def dropout(x: torch.Tensor, p: float, seed: int, offset: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    _req(x, "dropout input")
+    if not x.is_contiguous():
+        raise RuntimeError("omnibiote_b200: dropout input must be contiguous")
+    if out is None:
+        out = torch.empty_like(x)
+    rc = _lib.load().obt_dropout(x.data_ptr(), out.data_ptr(), x.numel(), float(p), seed, offset, _stream())
+    _lib.check(rc, "obt_dropout")
+    return out
+
+
+def scale_div(x: torch.Tensor, div: float) -> torch.Tensor:
+    _req(x, "scale_div input")
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    rc = _lib.load().obt_scale_div(x.data_ptr(), out.data_ptr(), x.numel(), float(div), _stream())
+    _lib.check(rc, "obt_scale_div")
+    return out
+
+
+def pool(emb: torch.Tensor, mode: str) -> torch.Tensor:
+    _req(emb, "emb")
+    emb = emb.contiguous()
+    B, T, C = emb.shape
+    lib = _lib.load()
+    out = torch.empty((B, C), dtype=torch.bfloat16, device=emb.device)
+    ws = workspace("pool", B * lib.obt_pool_splits(T) * C, torch.float32, emb.device)
+    rc = lib.obt_pool(emb.data_ptr(), out.data_ptr(), ws.data_ptr(), B, T, C, {"mean": 0, "max": 1}[mode], _stream())
+    _lib.check(rc, "obt_pool")
+    return out
+
+
+def pool_bwd(emb, pooled, dout, mode: str) -> torch.Tensor:
+    B, T, C = emb.shape
+    demb = torch.empty_like(emb)
+    rc = _lib.load().obt_pool_bwd(emb.data_ptr(), pooled.data_ptr(), dout.contiguous().data_ptr(), demb.data_ptr(), B,
+                                  T, C, {"mean": 0, "max": 1}[mode], _stream())
+    _lib.check(rc, "obt_pool_bwd")
+    return demb
+
+
+class MaskSpec:
+    """Additive attention mask as the kernels consume it: a bf16 tensor plus (batch, head, query) strides."""
+
+    __slots__ = ("tensor", "msb", "msh", "msq", "row_lo", "row_hi")
+
+    def __init__(self, attn_mask: torch.Tensor | None, B: int, H: int, T: int, row_lo=None, row_hi=None):
+        self.tensor = None
+        self.msb = self.msh = self.msq = 0
+        # optional interval form (int32 [B,T] each): key j visible to query (b,i) iff lo <= j < hi
+        self.row_lo, self.row_hi = row_lo, row_hi
+        if attn_mask is None:
+            return
+        m = attn_mask
+        if m.dim() != 4 or m.shape[0] != B or m.shape[-2] != T or m.shape[-1] != T or m.shape[1] not in (1, H):
+            raise RuntimeError(f"omnibiote_b200: attn_mask must be (b, n_head, t, t), got {tuple(m.shape)}")
+        if not m.is_cuda:
+            raise RuntimeError("omnibiote_b200: attn_mask must be a CUDA tensor")
+        if m.dtype != torch.bfloat16 or m.stride(-1) != 1:
+            # keep head-expanded (stride-0) views cheap: convert the un-expanded slice only
+            if m.stride(1) == 0 or m.shape[1] == 1:
+                m = m[:, :1].to(torch.bfloat16).contiguous().expand(-1, H, -1, -1)
+            else:
+                m = m.to(torch.bfloat16).contiguous()
+        self.tensor = m
+        self.msb = m.stride(0)
+        self.msh = m.stride(1) if m.shape[1] > 1 else 0
+        self.msq = m.stride(2)
+
+
+def attention_fwd(qkv: torch.Tensor, B: int, T: int, H: int, d: int, scale: float, mask: MaskSpec, drop_p: float,
+                  seed: int, offset: int, impl: str = "auto"):
+    """qkv [M,3C] (post-rotary) -> (y [M,C], lse [B,H,T,2])."""
+    qkv, ld = _mat(qkv, "qkv")
+    C = H * d
+    M = B * T
+    y = torch.empty((M, C), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((B, H, T, 2), dtype=torch.float32, device=qkv.device)
+    esz = 2
+    q, k, v = qkv.data_ptr(), qkv.data_ptr() + C * esz, qkv.data_ptr() + 2 * C * esz
+    lib = _lib.load()
+    use_iv = mask.tensor is None and mask.row_lo is not None
+    rc = lib.obt_attn_simt_fwd(q, k, v, ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
+                               _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0, y.data_ptr(), C,
+                               lse.data_ptr(), B, H, T, d, scale, float(drop_p), seed, offset, _stream())
+    _lib.check(rc, "obt_attn_simt_fwd")
+    return y, lse
+
+
+def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, seed, offset, impl: str = "auto"):
+    """Returns dqkv [M,3C] (gradient w.r.t. the post-rotary q,k and v)."""
+    qkv, ld = _mat(qkv, "qkv")
+    dy, lddy = _mat(dy, "attention dy")
+    C = H * d
+    M = B * T
+    dqkv = torch.empty((M, 3 * C), dtype=torch.bfloat16, device=qkv.device)
+    delta = torch.empty((B, H, T), dtype=torch.float32, device=qkv.device)
+    esz = 2
+    q, k, v = qkv.data_ptr(), qkv.data_ptr() + C * esz, qkv.data_ptr() + 2 * C * esz
+    dq, dk, dv = dqkv.data_ptr(), dqkv.data_ptr() + C * esz, dqkv.data_ptr() + 2 * C * esz
+    use_iv = mask.tensor is None and mask.row_lo is not None
+    rc = _lib.load().obt_attn_simt_bwd(q, k, v, ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
+                                       _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0,
+                                       y.data_ptr(), C, dy.data_ptr(), lddy, lse.data_ptr(), delta.data_ptr(), dq, dk,
+                                       dv, 3 * C, B, H, T, d, scale, float(drop_p), seed, offset, _stream())
+    _lib.check(rc, "obt_attn_simt_bwd")
+    return dqkv
+
+
+def ce_fwd(logits: torch.Tensor, targets: torch.Tensor, row_mask: torch.Tensor | None, n_acc: float):
+    """Returns (scalars[4] fp32 device: loss, count, dloss/dCE; lse [M]; tok_loss [M])."""
+    logits, ld = _mat(logits, "logits")
+    M, V = logits.shape
+    dev = logits.device
+    lse = torch.empty(M, dtype=torch.float32, device=dev)
+    tok = torch.empty(M, dtype=torch.float32, device=dev)
+    scalars = torch.empty(4, dtype=torch.float32, device=dev)
+    if row_mask is not None:
+        row_mask = row_mask.reshape(-1).to(torch.uint8).contiguous()
+    targets = targets.reshape(-1).contiguous()
+    rc = _lib.load().obt_ce_fwd(logits.data_ptr(), ld, targets.data_ptr(), _ptr(row_mask), lse.data_ptr(),
+                                tok.data_ptr(), scalars.data_ptr(), M, V, float(n_acc), _stream())
+    _lib.check(rc, "obt_ce_fwd")
+    return scalars, lse, tok, row_mask, targets
+
+
+def ce_bwd_(logits, targets, row_mask, lse, scalars, upstream: float = 1.0):
+    logits, ld = _mat(logits, "logits")
+    M, V = logits.shape
+    rc = _lib.load().obt_ce_bwd(logits.data_ptr(), ld, targets.data_ptr(), _ptr(row_mask), lse.data_ptr(),
+                                scalars.data_ptr(), float(upstream), M, V, _stream())
+    _lib.check(rc, "obt_ce_bwd")
+    return logits
+
+
+def doc_mask_intervals(ids: torch.Tensor, eos_token: int = 3, padding: bool = False):
+    """Per-token visible key interval of the reference's create_attention_mask (train_encoder.py:25-57)."""
+    _req(ids, "ids", torch.int64)
+    ids = ids.contiguous()
+    B, T = ids.shape
+    lo = torch.empty((B, T), dtype=torch.int32, device=ids.device)
+    hi = torch.empty((B, T), dtype=torch.int32, device=ids.device)
+    rc = _lib.load().obt_doc_mask_intervals(ids.data_ptr(), lo.data_ptr(), hi.data_ptr(), B, T, int(eos_token),
+                                            int(padding), _stream())
+    _lib.check(rc, "obt_doc_mask_intervals")
+    return lo, hi
+
+
+def pad_mask_intervals(ids: torch.Tensor, pad_token: int = 1):
+    """Interval form of evals/gue.py:15-21 pad_attn."""
+    _req(ids, "ids", torch.int64)
+    ids = ids.contiguous()
+    B, T = ids.shape
+    lo = torch.empty((B, T), dtype=torch.int32, device=ids.device)
+    hi = torch.empty((B, T), dtype=torch.int32, device=ids.device)
+    rc = _lib.load().obt_pad_mask_intervals(ids.data_ptr(), lo.data_ptr(), hi.data_ptr(), B, T, int(pad_token), _stream())
+    _lib.check(rc, "obt_pad_mask_intervals")
+    return lo, hi
+
+
+def mask_from_intervals(lo: torch.Tensor, hi: torch.Tensor) -> torch.Tensor:
+    """Dense additive bf16 (B,T,T) mask with values {0, -1e9}."""
+    B, T = lo.shape
+    mask = torch.empty((B, T, T), dtype=torch.bfloat16, device=lo.device)
+    rc = _lib.load().obt_mask_from_intervals(lo.data_ptr(), hi.data_ptr(), mask.data_ptr(), B, T, _stream())
+    _lib.check(rc, "obt_mask_from_intervals")
+    return mask
+
+
+def mask_compress(mask: torch.Tensor):
+    """Dense additive bf16 mask (B,T,T) or (B,H,T,T) head-broadcast -> (lo, hi, not_interval_flag[int32 device])."""
+    _req(mask, "mask")
+    if mask.dim() == 4:
+        mask = mask[:, 0]
+    if mask.stride(-1) != 1:
+        mask = mask.contiguous()
+    B, T, _ = mask.shape
+    lo = torch.empty((B, T), dtype=torch.int32, device=mask.device)
+    hi = torch.empty((B, T), dtype=torch.int32, device=mask.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=mask.device)
+    rc = _lib.load().obt_mask_compress(mask.data_ptr(), mask.stride(0), mask.stride(1), lo.data_ptr(), hi.data_ptr(),
+                                       flag.data_ptr(), B, T, _stream())
+    _lib.check(rc, "obt_mask_compress")
+    return lo, hi, flag
