@@ -104,6 +104,11 @@ int obt_attn_simt_bwd(const void* q, const void* k, const void* v, long long ld,
                       long long ldd, int B, int H, int T, int d, float scale, float drop_p, unsigned long long seed,
                       unsigned long long offset, cudaStream_t stream);
 
+/* tensor-core (tcgen05/TMEM/TMA) forward for head_dim == 128; qkv is the fused [M,3C] buffer (q | k | v). */
+int obt_attn_tc_fwd(const void* qkv, long long ld, const void* mask, long long msb, long long msh, long long msq,
+                    const int* row_lo, const int* row_hi, void* y, long long ldy, float* lse, int B, int H, int T, int d,
+                    float scale, float drop_p, unsigned long long seed, unsigned long long offset, cudaStream_t stream);
+
 /* ---- attention-mask producers / compressors (input contract of the hot path) ------------------------------------
  * obt_doc_mask_intervals : per (b,i) visible key interval [lo,hi) from token ids = create_attention_mask
  *                          (train_encoder.py:25-57) incl. its quirks; lo >= hi marks a fully-masked row.
@@ -118,6 +123,12 @@ int obt_pad_mask_intervals(const long long* ids, int* lo, int* hi, int B, int T,
 int obt_mask_from_intervals(const int* lo, const int* hi, void* mask, int B, int T, cudaStream_t stream);
 int obt_mask_compress(const void* mask, long long msb, long long msq, int* lo, int* hi, int* not_interval, int B, int T,
                       cudaStream_t stream);
+
+/* ---- MLM input masking (train_encoder.py:273-279): mask = Bernoulli(prob) & id != PAD & id != EOS;
+ * masked_ids = mask ? MASK : id. Device Philox stream instead of the reference's host numpy RNG. */
+int obt_mlm_mask(const long long* ids, long long* masked_ids, unsigned char* mask, long long n, float prob,
+                 unsigned long long seed, unsigned long long offset, long long pad_token, long long eos_token,
+                 long long mask_token, cudaStream_t stream);
 
 /* ---- MLM loss (train_encoder.py:301-305) over materialised logits ----------------------------------------------
  * scalars (device fp32[4]): [0] loss, [1] number of masked tokens, [2] d loss / d CE_t. row_mask: uint8 [M] or NULL. */
@@ -135,7 +146,7 @@ int obt_opt_meta_bytes(void);
 int obt_grad_norm(const void* metas, const int* blk_tensor, const long long* blk_off, int n_blocks, float gscale,
                   float max_norm, float* partial, float* norm_out, cudaStream_t stream);
 int obt_adamw_step(const void* metas, const int* blk_tensor, const long long* blk_off, int n_blocks,
-                   const float* clip_scalars, float gscale, float lr_mult, float beta1, float beta2, float eps, int step,
+                   const float* clip_scalars, float gscale, float lr_mult, double beta1, double beta2, double eps, int step,
                    int zero_grad, cudaStream_t stream);
 
 #ifdef __cplusplus

@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_longlong, c_ulonglong, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_ulonglong, c_void_p
 from pathlib import Path
 
 from . import build as _build
@@ -39,16 +39,19 @@ SIGNATURES = {
                                 u64, u64, vp]),
     "obt_attn_simt_bwd": (i32, [vp, vp, vp, i64, vp, i64, i64, i64, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, i64,
                                 i32, i32, i32, i32, f32, f32, u64, u64, vp]),
+    "obt_attn_tc_fwd": (i32, [vp, i64, vp, i64, i64, i64, vp, vp, vp, i64, vp, i32, i32, i32, i32, f32, f32, u64, u64,
+                              vp]),
     "obt_doc_mask_intervals": (i32, [vp, vp, vp, i32, i32, i64, i32, vp]),
     "obt_pad_mask_intervals": (i32, [vp, vp, vp, i32, i32, i64, vp]),
     "obt_mask_from_intervals": (i32, [vp, vp, vp, i32, i32, vp]),
     "obt_mask_compress": (i32, [vp, i64, i64, vp, vp, vp, i32, i32, vp]),
+    "obt_mlm_mask": (i32, [vp, vp, vp, i64, f32, u64, u64, i64, i64, i64, vp]),
     "obt_ce_fwd": (i32, [vp, i64, vp, vp, vp, vp, vp, i64, i32, f32, vp]),
     "obt_ce_bwd": (i32, [vp, i64, vp, vp, vp, vp, f32, i64, i32, vp]),
     "obt_opt_chunk_elems": (i32, []),
     "obt_opt_meta_bytes": (i32, []),
     "obt_grad_norm": (i32, [vp, vp, vp, i32, f32, f32, vp, vp, vp]),
-    "obt_adamw_step": (i32, [vp, vp, vp, i32, vp, f32, f32, f32, f32, f32, i32, i32, vp]),
+    "obt_adamw_step": (i32, [vp, vp, vp, i32, vp, f32, f32, c_double, c_double, c_double, i32, i32, vp]),
 }
 
 

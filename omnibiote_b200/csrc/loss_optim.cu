@@ -212,8 +212,8 @@ __global__ void gradnorm_final_kernel(const float* __restrict__ partial, int n, 
 //   p  = rb(p - (lr/(1-b1^t)) * (m / den))
 __global__ void adamw_kernel(const ParamMeta* __restrict__ metas, const int* __restrict__ blk_tensor,
                              const long long* __restrict__ blk_off, const float* __restrict__ clip_scalars,
-                             float gscale, float lr_mult, float beta1, float beta2, float eps, float bc1,
-                             float bc2_sqrt, int zero_grad) {
+                             float gscale, float lr_mult, float one_minus_b1, float beta2, float one_minus_b2,
+                             float eps, float bc1, float bc2_sqrt, int zero_grad) {
   const ParamMeta pm = metas[blk_tensor[blockIdx.x]];
   const long long off = blk_off[blockIdx.x];
   const long long n = min(static_cast<long long>(OPT_CHUNK), pm.numel - off);
@@ -229,8 +229,8 @@ __global__ void adamw_kernel(const ParamMeta* __restrict__ metas, const int* __r
     g = gscale == 1.0f ? g : rb(g * gscale);
     g = rb(g * clip);
     p = rb(p * decay);
-    m = rb(m + (1.0f - beta1) * (g - m));
-    v = rb(rb(v * beta2) + (1.0f - beta2) * g * g);
+    m = rb(m + one_minus_b1 * (g - m));
+    v = rb(rb(v * beta2) + one_minus_b2 * g * g);
     const float den = rb(rb(rb(sqrtf(v)) / bc2_sqrt) + eps);
     p = rb(p - step * (m / den));
   };
@@ -313,13 +313,16 @@ extern "C" int obt_grad_norm(const void* metas, const int* blk_tensor, const lon
 }
 
 extern "C" int obt_adamw_step(const void* metas, const int* blk_tensor, const long long* blk_off, int n_blocks,
-                              const float* clip_scalars, float gscale, float lr_mult, float beta1, float beta2,
-                              float eps, int step, int zero_grad, cudaStream_t stream) {
+                              const float* clip_scalars, float gscale, float lr_mult, double beta1, double beta2,
+                              double eps, int step, int zero_grad, cudaStream_t stream) {
   OBT_REQUIRE(metas && blk_tensor && blk_off, "obt_adamw_step: null pointer");
   OBT_REQUIRE(n_blocks > 0 && step >= 1, "obt_adamw_step: bad n_blocks=%d step=%d", n_blocks, step);
-  const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), static_cast<double>(step)));
-  const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), static_cast<double>(step))));
+  const float bc1 = static_cast<float>(1.0 - pow(beta1, static_cast<double>(step)));
+  const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(beta2, static_cast<double>(step))));
+  // (1 - beta) is formed in double like the reference's Python floats, then narrowed once
   adamw_kernel<<<n_blocks, 256, 0, stream>>>(static_cast<const ParamMeta*>(metas), blk_tensor, blk_off, clip_scalars,
-                                             gscale, lr_mult, beta1, beta2, eps, bc1, bc2_sqrt, zero_grad);
+                                             gscale, lr_mult, static_cast<float>(1.0 - beta1),
+                                             static_cast<float>(beta2), static_cast<float>(1.0 - beta2),
+                                             static_cast<float>(eps), bc1, bc2_sqrt, zero_grad);
   return check_launch("adamw");
 }

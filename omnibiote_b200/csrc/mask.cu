@@ -182,3 +182,42 @@ extern "C" int obt_mask_compress(const void* mask, long long msb, long long msq,
       static_cast<const __nv_bfloat16*>(mask), msb, msq, lo, hi, not_interval, B, T);
   return check_launch("mask_compress");
 }
+
+// ---------------------------------------------------------------------------------------------
+// MLM input masking on device (train_encoder.py:273-279): mask = Bernoulli(p) & id != PAD & id != EOS;
+// masked inputs get MASK_TOKEN (no 80/10/10 split in the reference). Philox instead of numpy's host RNG.
+// ---------------------------------------------------------------------------------------------
+namespace obt {
+__global__ void mlm_mask_kernel(const long long* __restrict__ ids, long long* __restrict__ masked,
+                                unsigned char* __restrict__ mask, long long n, float prob, unsigned long long seed,
+                                unsigned long long offset, long long pad, long long eos, long long mask_token) {
+  for (long long i4 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i4 * 4 < n;
+       i4 += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint4 r = philox4x32(seed, static_cast<unsigned long long>(i4), offset);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long i = i4 * 4 + e;
+      if (i >= n) break;
+      const long long id = ids[i];
+      const bool m = ((w[e] >> 8) * (1.0f / 16777216.0f) < prob) && id != pad && id != eos;
+      mask[i] = m ? 1 : 0;
+      masked[i] = m ? mask_token : id;
+    }
+  }
+}
+}  // namespace obt
+
+extern "C" int obt_mlm_mask(const long long* ids, long long* masked_ids, unsigned char* mask, long long n, float prob,
+                            unsigned long long seed, unsigned long long offset, long long pad_token, long long eos_token,
+                            long long mask_token, cudaStream_t stream) {
+  OBT_REQUIRE(ids && masked_ids && mask, "obt_mlm_mask: null pointer");
+  OBT_REQUIRE(prob >= 0.f && prob <= 1.f, "obt_mlm_mask: prob=%f", prob);
+  if (n == 0) return OBT_OK;
+  long long blocks = ((n + 3) / 4 + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  obt::mlm_mask_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(ids, masked_ids, mask, n, prob, seed, offset,
+                                                                        pad_token, eos_token, mask_token);
+  return check_launch("mlm_mask");
+}

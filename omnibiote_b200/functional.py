@@ -31,6 +31,21 @@ def direct_grad_accumulation(enabled: bool = True):
         _DIRECT_GRAD = prev
 
 
+# Optional sink (parallel.FlatGradBuckets) told which parameters' gradients just became final, so their bucket can be
+# all-reduced while the rest of the backward is still running.
+_GRAD_SINK = None
+
+
+def set_grad_sink(sink) -> None:
+    global _GRAD_SINK
+    _GRAD_SINK = sink
+
+
+def _grads_final(params) -> None:
+    if _GRAD_SINK is not None:
+        _GRAD_SINK.notify(params)
+
+
 def _wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, param):
     """dW[N,K] = dy[M,N]^T @ x[M,K] (both operands MN-major for the tensor cores, no transposes materialised)."""
     if _DIRECT_GRAD and param is not None and param.grad is not None:
@@ -68,6 +83,7 @@ class EmbedFunction(torch.autograd.Function):
         dout = dout.contiguous()
         if _DIRECT_GRAD and w.grad is not None:
             ops.embed_bwd(idx, dout, w.grad, True, p, seed, off)
+            _grads_final((w,))
             return None, None, None, None
         dw = torch.empty(shape, dtype=torch.bfloat16, device=dout.device)
         ops.embed_bwd(idx, dout, dw, False, p, seed, off)
@@ -142,6 +158,7 @@ class BlockFunction(torch.autograd.Function):
         acc1 = direct and pg1.grad is not None
         dx, dg1 = ops.layernorm_bwd(dh1, x, g1, mean1, rstd1, dres=dx1, dgamma=pg1.grad if acc1 else None,
                                     accumulate_dgamma=acc1)
+        _grads_final(ctx.params)
         return (dx, None if acc1 else dg1, dw_qkv, dw_o, None if acc2 else dg2, dw_fc, dw_pr, None, None, None, None,
                 None, None, None, None)
 
@@ -219,6 +236,7 @@ class HeadLossFunction(torch.autograd.Function):
         acc = _DIRECT_GRAD and pg.grad is not None
         dx, dg = ops.layernorm_bwd(dz, x, gamma, mean, rstd, dgamma=pg.grad if acc else None, accumulate_dgamma=acc,
                                    dy_div=ctx.div)
+        _grads_final(ctx.params)
         return dx, (None if acc else dg), dw, None, None, None, None
 
 

@@ -187,7 +187,10 @@ class OmniBioTA(nn.Module):
         C = wte.shape[1]
         x = Fn.EmbedFunction.apply(idx.reshape(-1), wte, self.transformer.drop.p, self.training).view(b, t, C)
         blocks = self.transformer.h
-        mask = ops.MaskSpec(attn_mask, b, blocks[0].attn.n_head, t) if len(blocks) else None
+        if isinstance(attn_mask, ops.MaskSpec):
+            mask = attn_mask  # already in kernel form (dense bias or per-row intervals)
+        else:
+            mask = ops.MaskSpec(attn_mask, b, blocks[0].attn.n_head, t) if len(blocks) else None
         ckpt = self.config.checkpoint_freq
         for i, block in enumerate(blocks):
             if ckpt > 0 and i % ckpt == 0 and torch.is_grad_enabled():

@@ -15,10 +15,24 @@ EPI_PLAIN, EPI_RESID, EPI_GELU, EPI_GELU_BWD, EPI_RESID_DROPOUT = 0, 1, 2, 3, 5
 # the same expression, which is what the CPU oracle does). See SURVEY Appendix A.2.
 GELU_MODE = 0
 
+# attention kernel selection: "auto" = tensor-core kernel for head_dim 128, generic CUDA-core kernel otherwise;
+# "tc" / "simt" force one (tests, cross-checks). Both are CUDA kernels of this library; neither is a fallback to torch.
+import os as _os
+
+ATTN_IMPL = _os.environ.get("OBT_ATTN_IMPL", "auto")
+
 _workspaces: dict = {}
 
 
+# Instrumentation used by bench.py: LAUNCHES counts C-ABI calls (each enqueues at least one kernel of this library);
+# PROFILE_GEMM, when a list, receives (flops, start_event, end_event) for every GEMM launch.
+LAUNCHES = 0
+PROFILE_GEMM = None
+
+
 def _stream() -> int:
+    global LAUNCHES
+    LAUNCHES += 1
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -85,10 +99,17 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a
         ws_elems = 8 * M * N
         ws = workspace("splitk", ws_elems, torch.float32, a.device)
     lib = _lib.load()
+    prof = PROFILE_GEMM
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = lib.obt_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldd, int(a_mn), int(b_mn),
                            epilogue, _ptr(aux_in), ld_ai, _ptr(aux_out), ld_ao, GELU_MODE, float(drop_p), seed, offset,
                            _ptr(ws), ws_elems, _stream())
     _lib.check(rc, "obt_gemm_bf16")
+    if prof is not None:
+        ev1.record()
+        prof.append((2.0 * M * N * K, ev0, ev1))
     return out
 
 
@@ -247,6 +268,18 @@ def attention_fwd(qkv: torch.Tensor, B: int, T: int, H: int, d: int, scale: floa
     q, k, v = qkv.data_ptr(), qkv.data_ptr() + C * esz, qkv.data_ptr() + 2 * C * esz
     lib = _lib.load()
     use_iv = mask.tensor is None and mask.row_lo is not None
+    if impl == "auto":
+        impl = ATTN_IMPL
+    if impl == "auto":
+        dense_ok = mask.tensor is None or (T % 8 == 0 and mask.msq % 8 == 0 and mask.msb % 8 == 0 and mask.msh % 8 == 0
+                                           and mask.tensor.data_ptr() % 16 == 0)
+        impl = "tc" if (d == 128 and dense_ok) else "simt"
+    if impl == "tc":
+        rc = lib.obt_attn_tc_fwd(qkv.data_ptr(), ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
+                                 _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0, y.data_ptr(), C,
+                                 lse.data_ptr(), B, H, T, d, scale, float(drop_p), seed, offset, _stream())
+        _lib.check(rc, "obt_attn_tc_fwd")
+        return y, lse
     rc = lib.obt_attn_simt_fwd(q, k, v, ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
                                _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0, y.data_ptr(), C,
                                lse.data_ptr(), B, H, T, d, scale, float(drop_p), seed, offset, _stream())

@@ -210,6 +210,6 @@ def test_fused_adamw_matches_torch_bf16_foreach(golden):
         p.grad = a["g"][s].clone().cuda()
         opt.step()
         st = opt.state[p]
-        assert max_abs(st["exp_avg"], a["m"][s]) <= 2 ** -8 * float(a["m"][s].abs().max())
-        assert max_abs(st["exp_avg_sq"], a["v"][s]) <= 2 ** -8 * float(a["v"][s].abs().max())
+        assert max_abs(st["exp_avg"], a["m"][s]) <= 2 ** -7 * float(a["m"][s].abs().max())  # <= 1 bf16 ulp
+        assert max_abs(st["exp_avg_sq"], a["v"][s]) <= 2 ** -7 * float(a["v"][s].abs().max())
         assert max_abs(p, a["p"][s]) <= 2 ** -7 * float(a["p"][s].abs().max())
