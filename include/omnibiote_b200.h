@@ -109,6 +109,13 @@ int obt_attn_tc_fwd(const void* qkv, long long ld, const void* mask, long long m
                     const int* row_lo, const int* row_hi, void* y, long long ldy, float* lse, int B, int H, int T, int d,
                     float scale, float drop_p, unsigned long long seed, unsigned long long offset, cudaStream_t stream);
 
+/* tensor-core backward (head_dim == 128): delta pre-pass + dQ kernel + dK/dV kernel. dqkv is the fused [M,3C]
+ * gradient buffer (dq | dk | dv, pitch ldd); delta is fp32 [B,H,T] scratch; autograd adjoint of model.py:111-148. */
+int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, long long msb, long long msh, long long msq,
+                    const int* row_lo, const int* row_hi, const void* y, long long ldy, const void* dy, long long lddy,
+                    const float* lse, float* delta, void* dqkv, long long ldd, int B, int H, int T, int d, float scale,
+                    float drop_p, unsigned long long seed, unsigned long long offset, cudaStream_t stream);
+
 /* ---- attention-mask producers / compressors (input contract of the hot path) ------------------------------------
  * obt_doc_mask_intervals : per (b,i) visible key interval [lo,hi) from token ids = create_attention_mask
  *                          (train_encoder.py:25-57) incl. its quirks; lo >= hi marks a fully-masked row.

@@ -41,6 +41,8 @@ SIGNATURES = {
                                 i32, i32, i32, i32, f32, f32, u64, u64, vp]),
     "obt_attn_tc_fwd": (i32, [vp, i64, vp, i64, i64, i64, vp, vp, vp, i64, vp, i32, i32, i32, i32, f32, f32, u64, u64,
                               vp]),
+    "obt_attn_tc_bwd": (i32, [vp, i64, vp, i64, i64, i64, vp, vp, vp, i64, vp, i64, vp, vp, vp, i64, i32, i32, i32, i32,
+                              f32, f32, u64, u64, vp]),
     "obt_doc_mask_intervals": (i32, [vp, vp, vp, i32, i32, i64, i32, vp]),
     "obt_pad_mask_intervals": (i32, [vp, vp, vp, i32, i32, i64, vp]),
     "obt_mask_from_intervals": (i32, [vp, vp, vp, i32, i32, vp]),

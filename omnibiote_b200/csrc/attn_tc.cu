@@ -14,32 +14,9 @@
 // Mask modes: none | per-row visible key interval [lo,hi) (document / padding masks; KV tiles outside the union of
 // the tile's intervals are skipped) | dense additive bf16 bias (arbitrary masks). Fully-masked rows (finite -1e9 on
 // every key) attend uniformly to all T keys like the reference.
-#include "common.cuh"
-#include "ptx.cuh"
+#include "attn_tc_common.cuh"
 
 namespace obt {
-
-constexpr int ATT_D = 128;      // head dim
-constexpr int ATT_BM = 128;     // query rows per CTA
-constexpr int ATT_BN = 128;     // keys per KV tile
-constexpr uint32_t ATT_TILE_BYTES = 128 * 128 * 2;  // one [128 x 128] bf16 operand tile = two 16 KB swizzle sub-tiles
-constexpr float LOG2E = 1.4426950408889634f;
-
-struct AttnTcParams {
-  int B, H, T;
-  float scale;
-  // mask
-  const __nv_bfloat16* mask;  // dense additive bias or nullptr
-  long long msb, msh, msq;
-  const int* row_lo;  // interval mode or nullptr
-  const int* row_hi;
-  // outputs
-  __nv_bfloat16* y;
-  long long ldy;
-  float* lse;  // [B,H,T,2] (row max, log exp-sum) in natural-log units of the scaled+biased scores
-  float drop_p;
-  unsigned long long seed, offset;
-};
 
 struct AttnFwdSmem {
   static constexpr uint32_t Q_OFF = 0;
@@ -49,41 +26,6 @@ struct AttnFwdSmem {
   static constexpr uint32_t BAR_OFF = P_OFF + ATT_TILE_BYTES;
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
-
-// byte offset of the 16-byte chunk holding elements [c, c+8) of row r inside a [128 x 128] bf16 tile stored as two
-// [128 x 64] K-major sub-tiles with the 128B swizzle (what TMA SWIZZLE_128B produces and UMMA descriptors expect)
-__device__ __forceinline__ uint32_t sw128_chunk_off(int r, int c) {
-  const int sub = c >> 6;
-  const int chunk = (c & 63) >> 3;
-  return static_cast<uint32_t>(sub * 16384 + r * 128 + ((chunk ^ (r & 7)) << 4));
-}
-
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-__device__ __forceinline__ float keep_scale_tc(const AttnTcParams& p, int b, int h, int i, int j) {
-  const unsigned long long e = ((static_cast<unsigned long long>(b) * p.H + h) * p.T + i) * p.T + j;
-  uint4 r = philox4x32(p.seed, e >> 2, p.offset);
-  const uint32_t w = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
-  return ((w >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 1.0f / (1.0f - p.drop_p) : 0.f;
-}
-
-// Issue the 8 UMMA (k = 16 each) of one 128x128x128 product.
-//   a_addr: K-major A tile (two 64-wide sub-tiles); b_addr: B tile, K-major (b_mn = false) or MN-major (b_mn = true).
-template <bool kBMN>
-__device__ __forceinline__ void issue_128x128x128(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, bool accumulate) {
-  constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, kBMN);
-#pragma unroll
-  for (int kk = 0; kk < 8; ++kk) {
-    const uint64_t a_desc = make_smem_desc_sw128(a_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024);
-    const uint64_t b_desc = kBMN ? make_smem_desc_sw128(b_addr + kk * 2048, 16384, 1024)
-                                 : make_smem_desc_sw128(b_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024);
-    umma_bf16_ss<1>(d_tmem, a_desc, b_desc, idesc, (accumulate || kk > 0) ? 1u : 0u);
-  }
-}
 
 __global__ void __launch_bounds__(192, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParams p, int C) {

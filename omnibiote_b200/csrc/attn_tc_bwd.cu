@@ -1,0 +1,571 @@
+// Attention backward on tcgen05 tensor cores (head_dim = 128): the adjoint of attn_tc.cu.
+//
+//   delta_i = dO_i . O_i                                   (attn_delta_kernel, memory-bound pre-pass)
+//   dQ kernel : one CTA per 128-query tile, loops over KV tiles:  S = Q K^T, dP = dO V^T (TMEM),
+//               dS = P o (dP - delta) * scale -> bf16 smem tile,   dQ += dS K   (accumulated in TMEM)
+//   dKV kernel: one CTA per 128-key tile, loops over query tiles: S^T = K Q^T, dP^T = V dO^T (TMEM),
+//               P^T, dS^T -> bf16 smem tiles,   dV += P^T dO,   dK += dS^T Q   (accumulated in TMEM)
+// P is recomputed from the forward's (row max, log exp-sum) pair. Splitting dQ from dK/dV recomputes S and dP once
+// more (7 instead of 5 tile products) but needs no atomics and keeps every accumulator in TMEM.
+// The Q / dO / K / V smem tiles written by TMA serve both as K-major operands (scores) and, read through an
+// MN-major descriptor, as the [reduction x 128] operands of the gradient products: no transposes are materialised.
+#include "attn_tc_common.cuh"
+
+namespace obt {
+
+// ---------------------------------------------------------------------------------------------
+// delta[b,h,i] = sum_e dO[row, h*128+e] * O[row, h*128+e]; one warp per token row, loops over heads
+// ---------------------------------------------------------------------------------------------
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const __nv_bfloat16* __restrict__ y,
+                                  long long ldy, float* __restrict__ delta, int B, int H, int T) {
+  const int warps = blockDim.x >> 5;
+  const long long row = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5);
+  if (row >= static_cast<long long>(B) * T) return;
+  const int lane = threadIdx.x & 31;
+  const int b = static_cast<int>(row / T), i = static_cast<int>(row % T);
+  for (int h = 0; h < H; ++h) {
+    const uint2 a = *reinterpret_cast<const uint2*>(dy + row * lddy + h * ATT_D + lane * 4);
+    const uint2 c = *reinterpret_cast<const uint2*>(y + row * ldy + h * ATT_D + lane * 4);
+    float s = bf16_lo(a.x) * bf16_lo(c.x) + bf16_hi(a.x) * bf16_hi(c.x) + bf16_lo(a.y) * bf16_lo(c.y) +
+              bf16_hi(a.y) * bf16_hi(c.y);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) delta[(static_cast<long long>(b) * H + h) * T + i] = s;
+  }
+}
+
+// =============================================================================================
+// dQ kernel
+// =============================================================================================
+struct AttnDqSmem {
+  static constexpr uint32_t Q_OFF = 0;
+  static constexpr uint32_t DO_OFF = Q_OFF + ATT_TILE_BYTES;
+  static constexpr uint32_t K_OFF = DO_OFF + ATT_TILE_BYTES;      // 2 stages
+  static constexpr uint32_t V_OFF = K_OFF + 2 * ATT_TILE_BYTES;   // 2 stages
+  static constexpr uint32_t DS_OFF = V_OFF + 2 * ATT_TILE_BYTES;
+  static constexpr uint32_t BAR_OFF = DS_OFF + ATT_TILE_BYTES;
+  static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(192, 1)
+attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dy,
+                  const AttnTcParams p, int C) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + AttnDqSmem::Q_OFF;
+  uint8_t* sDO = smem + AttnDqSmem::DO_OFF;
+  uint8_t* sK = smem + AttnDqSmem::K_OFF;
+  uint8_t* sV = smem + AttnDqSmem::V_OFF;
+  uint8_t* sDS = smem + AttnDqSmem::DS_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnDqSmem::BAR_OFF);
+  uint64_t* qdo_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* sdp_full = bars + 9;
+  uint64_t* ds_full = bars + 10;
+  uint64_t* dq_done = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  int* s_range = reinterpret_cast<int*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = blockIdx.x * ATT_BM;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int T = p.T;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_dy);
+    mbar_init(qdo_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(ds_full, 4);
+    mbar_init(dq_done, 1);
+    fence_barrier_init();
+    s_range[0] = T;
+    s_range[1] = 0;
+    s_range[2] = 0;
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+  __syncthreads();
+  if (p.row_lo != nullptr && threadIdx.x < ATT_BM && t0 + static_cast<int>(threadIdx.x) < T) {
+    const int lo = p.row_lo[static_cast<long long>(b) * T + t0 + threadIdx.x];
+    const int hi = p.row_hi[static_cast<long long>(b) * T + t0 + threadIdx.x];
+    if (lo >= hi) {
+      atomicExch(&s_range[2], 1);
+    } else {
+      atomicMin(&s_range[0], lo);
+      atomicMax(&s_range[1], hi);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  int jb = 0, je = (T + ATT_BN - 1) / ATT_BN;
+  if (p.row_lo != nullptr && s_range[2] == 0 && s_range[1] > s_range[0]) {
+    jb = s_range[0] / ATT_BN;
+    je = (s_range[1] + ATT_BN - 1) / ATT_BN;
+  }
+  const int n_tiles = je - jb;
+  const int row0 = b * T;
+  const int qcol = h * ATT_D, kcol = C + h * ATT_D, vcol = 2 * C + h * ATT_D;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(qdo_full, 2 * ATT_TILE_BYTES);
+      tma_load_2d(&tm_qkv, qdo_full, sQ, qcol, row0 + t0);
+      tma_load_2d(&tm_qkv, qdo_full, sQ + 16384, qcol + 64, row0 + t0);
+      tma_load_2d(&tm_dy, qdo_full, sDO, qcol, row0 + t0);
+      tma_load_2d(&tm_dy, qdo_full, sDO + 16384, qcol + 64, row0 + t0);
+      for (int jj = 0; jj < n_tiles; ++jj) {
+        const int st = jj & 1;
+        const uint32_t par = (jj >> 1) & 1;
+        const int krow = row0 + (jb + jj) * ATT_BN;
+        mbar_wait(&k_empty[st], par ^ 1);
+        mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
+        tma_load_2d(&tm_qkv, &k_full[st], sK + st * ATT_TILE_BYTES, kcol, krow);
+        tma_load_2d(&tm_qkv, &k_full[st], sK + st * ATT_TILE_BYTES + 16384, kcol + 64, krow);
+        mbar_wait(&v_empty[st], par ^ 1);
+        mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
+        tma_load_2d(&tm_qkv, &v_full[st], sV + st * ATT_TILE_BYTES, vcol, krow);
+        tma_load_2d(&tm_qkv, &v_full[st], sV + st * ATT_TILE_BYTES + 16384, vcol + 64, krow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), ds_addr = smem_u32(sDS);
+      mbar_wait(qdo_full, 0);
+      for (int jj = 0; jj < n_tiles; ++jj) {
+        const int st = jj & 1;
+        const uint32_t par = (jj >> 1) & 1;
+        const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES), v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+        mbar_wait(&k_full[st], par);
+        mbar_wait(&v_full[st], par);
+        tc_fence_after();
+        issue_128x128x128<false>(tmem_base, q_addr, k_addr, false);         // S  = Q K^T
+        issue_128x128x128<false>(tmem_base + 128, do_addr, v_addr, false);  // dP = dO V^T
+        umma_commit(sdp_full);
+        mbar_wait(ds_full, jj & 1);
+        tc_fence_after();
+        issue_128x128x128<true>(tmem_base + 256, ds_addr, k_addr, jj > 0);  // dQ += dS K
+        umma_commit(dq_done);
+        umma_commit(&k_empty[st]);
+        umma_commit(&v_empty[st]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int i = t0 + r;
+    const bool row_ok = i < T;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    int lo = 0, hi = T;
+    float row_scale = p.scale;  // natural-log units here
+    if (p.row_lo != nullptr && row_ok) {
+      lo = p.row_lo[static_cast<long long>(b) * T + i];
+      hi = p.row_hi[static_cast<long long>(b) * T + i];
+      if (lo >= hi) { lo = 0; hi = T; row_scale = 0.f; }
+    }
+    const long long bh = static_cast<long long>(b) * p.H + h;
+    float off = 0.f, ls2 = 0.f, dl = 0.f;
+    if (row_ok) {
+      off = p.lse[2 * (bh * T + i)];
+      ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
+      dl = p.delta[bh * T + i];
+    }
+    const __nv_bfloat16* mrow =
+        (p.mask != nullptr && row_ok) ? p.mask + b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq : nullptr;
+    const bool use_drop = p.drop_p > 0.f;
+
+    for (int jj = 0; jj < n_tiles; ++jj) {
+      const int j0 = (jb + jj) * ATT_BN;
+      mbar_wait(sdp_full, jj & 1);
+      tc_fence_after();
+      if (jj > 0) mbar_wait(dq_done, (jj - 1) & 1);  // previous dS tile fully consumed
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32], dv[32];
+        __syncwarp();
+        tmem_ld_32x32(lane_addr + c * 32, sv);
+        tmem_ld_32x32(lane_addr + 128 + c * 32, dv);
+        tmem_ld_wait();
+        float ds[32];
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+          float ks[4] = {1.f, 1.f, 1.f, 1.f};
+          if (use_drop && row_ok)
+            keep4(p, ((static_cast<unsigned long long>(bh) * T + i) * T) + static_cast<unsigned long long>(j0 + c * 32 + g4 * 4), ks);
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const int e = g4 * 4 + e4;
+            const int j = j0 + c * 32 + e;
+            float sp;
+            bool vis;
+            if (mrow != nullptr) {
+              vis = j < T;
+              const float bias = vis ? __bfloat162float(mrow[j]) : 0.f;
+              sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
+            } else {
+              vis = (j >= lo && j < hi);
+              sp = __uint_as_float(sv[e]) * row_scale;
+            }
+            const float pr = (vis && row_ok) ? fast_exp2((sp - off) * LOG2E - ls2) : 0.f;
+            ds[e] = pr * (__uint_as_float(dv[e]) * ks[e4] - dl) * row_scale;
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 w = make_uint4(pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]), pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]),
+                                     pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]), pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(sDS + sw128_chunk_off(r, c * 32 + g * 8)) = w;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    }
+    mbar_wait(dq_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    __nv_bfloat16* drow = p.dq + (static_cast<long long>(row0) + i) * p.ldd + h * ATT_D;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      __syncwarp();
+      tmem_ld_32x32(lane_addr + 256 + c * 32, o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          reinterpret_cast<uint4*>(drow + c * 32)[g] = make_uint4(
+              pack_bf16x2(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1])),
+              pack_bf16x2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3])),
+              pack_bf16x2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5])),
+              pack_bf16x2(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7])));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// =============================================================================================
+// dK / dV kernel
+// =============================================================================================
+struct AttnDkvSmem {
+  static constexpr uint32_t K_OFF = 0;
+  static constexpr uint32_t V_OFF = K_OFF + ATT_TILE_BYTES;
+  static constexpr uint32_t Q_OFF = V_OFF + ATT_TILE_BYTES;
+  static constexpr uint32_t DO_OFF = Q_OFF + ATT_TILE_BYTES;
+  static constexpr uint32_t PT_OFF = DO_OFF + ATT_TILE_BYTES;
+  static constexpr uint32_t DST_OFF = PT_OFF + ATT_TILE_BYTES;
+  static constexpr uint32_t COL_OFF = DST_OFF + ATT_TILE_BYTES;  // per-query (column) parameters: 6 x 128 x 4 B
+  static constexpr uint32_t BAR_OFF = COL_OFF + 6 * 128 * 4;
+  static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(192, 1)
+attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dy,
+                   const AttnTcParams p, int C) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem + AttnDkvSmem::K_OFF;
+  uint8_t* sV = smem + AttnDkvSmem::V_OFF;
+  uint8_t* sQ = smem + AttnDkvSmem::Q_OFF;
+  uint8_t* sDO = smem + AttnDkvSmem::DO_OFF;
+  uint8_t* sPT = smem + AttnDkvSmem::PT_OFF;
+  uint8_t* sDST = smem + AttnDkvSmem::DST_OFF;
+  int* c_lo = reinterpret_cast<int*>(smem + AttnDkvSmem::COL_OFF);
+  int* c_hi = c_lo + 128;
+  float* c_scale = reinterpret_cast<float*>(c_hi + 128);
+  float* c_off = c_scale + 128;
+  float* c_ls2 = c_off + 128;
+  float* c_dl = c_ls2 + 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnDkvSmem::BAR_OFF);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qdo_full = bars + 1;
+  uint64_t* qdo_empty = bars + 2;
+  uint64_t* sdp_full = bars + 3;
+  uint64_t* pds_full = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  unsigned int* s_rel = reinterpret_cast<unsigned int*>(bars + 6);  // relevance bitmask of query tiles (<= 64 tiles)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = blockIdx.x * ATT_BN;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int T = p.T;
+  const int nq = (T + ATT_BM - 1) / ATT_BM;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_dy);
+    mbar_init(kv_full, 1);
+    mbar_init(qdo_full, 1);
+    mbar_init(qdo_empty, 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 4);
+    fence_barrier_init();
+    s_rel[0] = 0;
+    s_rel[1] = 0;
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+  __syncthreads();
+  // which query tiles can see this key tile at all
+  if (p.row_lo != nullptr) {
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+      const int lo = p.row_lo[static_cast<long long>(b) * T + i], hi = p.row_hi[static_cast<long long>(b) * T + i];
+      const bool rel = (lo >= hi) || (lo < j0 + ATT_BN && hi > j0);
+      if (rel) atomicOr(&s_rel[(i / ATT_BM) >> 5], 1u << ((i / ATT_BM) & 31));
+    }
+  } else if (threadIdx.x == 0) {
+    s_rel[0] = 0xffffffffu;
+    s_rel[1] = 0xffffffffu;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const unsigned long long rel = (static_cast<unsigned long long>(s_rel[1]) << 32) | s_rel[0];
+  const int row0 = b * T;
+  const int qcol = h * ATT_D, kcol = C + h * ATT_D, vcol = 2 * C + h * ATT_D;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * ATT_TILE_BYTES);
+      tma_load_2d(&tm_qkv, kv_full, sK, kcol, row0 + j0);
+      tma_load_2d(&tm_qkv, kv_full, sK + 16384, kcol + 64, row0 + j0);
+      tma_load_2d(&tm_qkv, kv_full, sV, vcol, row0 + j0);
+      tma_load_2d(&tm_qkv, kv_full, sV + 16384, vcol + 64, row0 + j0);
+      int n = 0;
+      for (int it = 0; it < nq; ++it) {
+        if (!((rel >> it) & 1ull)) continue;
+        mbar_wait(qdo_empty, (n & 1) ^ 1);
+        mbar_expect_tx(qdo_full, 2 * ATT_TILE_BYTES);
+        const int qrow = row0 + it * ATT_BM;
+        tma_load_2d(&tm_qkv, qdo_full, sQ, qcol, qrow);
+        tma_load_2d(&tm_qkv, qdo_full, sQ + 16384, qcol + 64, qrow);
+        tma_load_2d(&tm_dy, qdo_full, sDO, qcol, qrow);
+        tma_load_2d(&tm_dy, qdo_full, sDO + 16384, qcol + 64, qrow);
+        ++n;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
+      const uint32_t pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
+      mbar_wait(kv_full, 0);
+      int n = 0;
+      for (int it = 0; it < nq; ++it) {
+        if (!((rel >> it) & 1ull)) continue;
+        mbar_wait(qdo_full, n & 1);
+        tc_fence_after();
+        issue_128x128x128<false>(tmem_base, k_addr, q_addr, false);         // S^T  = K Q^T
+        issue_128x128x128<false>(tmem_base + 128, v_addr, do_addr, false);  // dP^T = V dO^T
+        umma_commit(sdp_full);
+        mbar_wait(pds_full, n & 1);
+        tc_fence_after();
+        issue_128x128x128<true>(tmem_base + 256, pt_addr, do_addr, n > 0);  // dV += P^T dO
+        issue_128x128x128<true>(tmem_base + 384, dst_addr, q_addr, n > 0);  // dK += dS^T Q
+        umma_commit(qdo_empty);
+        ++n;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // key row within the tile
+    const int j = j0 + r;
+    const bool key_ok = j < T;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const long long bh = static_cast<long long>(b) * p.H + h;
+    const bool use_drop = p.drop_p > 0.f;
+    int n = 0;
+    for (int it = 0; it < nq; ++it) {
+      if (!((rel >> it) & 1ull)) continue;
+      const int i0 = it * ATT_BM;
+      // per-query parameters of this tile (thread r loads query i0 + r)
+      compute_bar_sync();
+      {
+        const int i = i0 + r;
+        int lo = 0, hi = T;
+        float sc = p.scale, off = 0.f, ls2 = 0.f, dl = 0.f;
+        if (i < T) {
+          if (p.row_lo != nullptr) {
+            lo = p.row_lo[static_cast<long long>(b) * T + i];
+            hi = p.row_hi[static_cast<long long>(b) * T + i];
+            if (lo >= hi) { lo = 0; hi = T; sc = 0.f; }
+          }
+          off = p.lse[2 * (bh * T + i)];
+          ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
+          dl = p.delta[bh * T + i];
+        } else {
+          lo = 0; hi = 0;  // query beyond the sequence: contributes nothing
+        }
+        c_lo[r] = lo; c_hi[r] = hi; c_scale[r] = sc; c_off[r] = off; c_ls2[r] = ls2; c_dl[r] = dl;
+      }
+      compute_bar_sync();
+      mbar_wait(sdp_full, n & 1);
+      tc_fence_after();
+      if (n > 0) mbar_wait(qdo_empty, (n - 1) & 1);  // previous P^T / dS^T tiles fully consumed
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32], dv[32];
+        __syncwarp();
+        tmem_ld_32x32(lane_addr + c * 32, sv);
+        tmem_ld_32x32(lane_addr + 128 + c * 32, dv);
+        tmem_ld_wait();
+        float pt[32], dst[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int col = c * 32 + e;
+          const int i = i0 + col;
+          const float sc = c_scale[col];
+          float sp;
+          bool vis;
+          if (p.mask != nullptr) {
+            vis = key_ok && i < T;
+            const float bias = vis ? __bfloat162float(p.mask[b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq + j]) : 0.f;
+            sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
+          } else {
+            vis = key_ok && j >= c_lo[col] && j < c_hi[col];
+            sp = __uint_as_float(sv[e]) * sc;
+          }
+          const float pr = vis ? fast_exp2((sp - c_off[col]) * LOG2E - c_ls2[col]) : 0.f;
+          float ks = 1.0f;
+          if (use_drop && vis) {
+            const unsigned long long eidx = (static_cast<unsigned long long>(bh) * T + i) * T + j;
+            const uint4 rnd = philox4x32(p.seed, eidx >> 2, p.offset);
+            const uint32_t w = (eidx & 3) == 0 ? rnd.x : (eidx & 3) == 1 ? rnd.y : (eidx & 3) == 2 ? rnd.z : rnd.w;
+            ks = ((w >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 1.0f / (1.0f - p.drop_p) : 0.f;
+          }
+          pt[e] = pr * ks;
+          dst[e] = pr * (__uint_as_float(dv[e]) * ks - c_dl[col]) * sc;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t o = sw128_chunk_off(r, c * 32 + g * 8);
+          *reinterpret_cast<uint4*>(sPT + o) =
+              make_uint4(pack_bf16x2(pt[g * 8 + 0], pt[g * 8 + 1]), pack_bf16x2(pt[g * 8 + 2], pt[g * 8 + 3]),
+                         pack_bf16x2(pt[g * 8 + 4], pt[g * 8 + 5]), pack_bf16x2(pt[g * 8 + 6], pt[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(sDST + o) =
+              make_uint4(pack_bf16x2(dst[g * 8 + 0], dst[g * 8 + 1]), pack_bf16x2(dst[g * 8 + 2], dst[g * 8 + 3]),
+                         pack_bf16x2(dst[g * 8 + 4], dst[g * 8 + 5]), pack_bf16x2(dst[g * 8 + 6], dst[g * 8 + 7]));
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      ++n;
+    }
+    // epilogue: dV, dK rows of this key
+    __nv_bfloat16* dvrow = p.dv + (static_cast<long long>(row0) + j) * p.ldd + h * ATT_D;
+    __nv_bfloat16* dkrow = p.dk + (static_cast<long long>(row0) + j) * p.ldd + h * ATT_D;
+    if (n > 0) {
+      mbar_wait(qdo_empty, (n - 1) & 1);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      uint32_t o[32];
+      __syncwarp();
+      if (n > 0) {
+        tmem_ld_32x32(lane_addr + 256 + c * 32, o);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[e] = 0u;
+      }
+      if (key_ok) {
+        __nv_bfloat16* dst = (c < 4 ? dvrow : dkrow) + (c & 3) * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          reinterpret_cast<uint4*>(dst)[g] = make_uint4(
+              pack_bf16x2(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1])),
+              pack_bf16x2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3])),
+              pack_bf16x2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5])),
+              pack_bf16x2(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7])));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+}  // namespace obt
+
+using namespace obt;
+
+extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, long long msb, long long msh,
+                               long long msq, const int* row_lo, const int* row_hi, const void* y, long long ldy,
+                               const void* dy, long long lddy, const float* lse, float* delta, void* dqkv, long long ldd,
+                               int B, int H, int T, int d, float scale, float drop_p, unsigned long long seed,
+                               unsigned long long offset, cudaStream_t stream) {
+  OBT_REQUIRE(qkv && y && dy && lse && delta && dqkv, "obt_attn_tc_bwd: null pointer");
+  OBT_REQUIRE(d == ATT_D, "obt_attn_tc_bwd: head_dim=%d, the tensor-core kernel is specialised for 128", d);
+  OBT_REQUIRE(B > 0 && H > 0 && T > 0, "obt_attn_tc_bwd: empty problem");
+  OBT_REQUIRE(T <= 64 * ATT_BM, "obt_attn_tc_bwd: T=%d exceeds %d", T, 64 * ATT_BM);
+  OBT_REQUIRE(ld % 8 == 0 && ldy % 8 == 0 && lddy % 8 == 0 && ldd % 8 == 0, "obt_attn_tc_bwd: pitches must be multiples of 8");
+  OBT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "obt_attn_tc_bwd: dropout p=%f", drop_p);
+  OBT_REQUIRE(drop_p == 0.f || T % 4 == 0, "obt_attn_tc_bwd: attention dropout needs T %% 4 == 0 (T=%d)", T);
+  const int C = H * d;
+  const long long M = static_cast<long long>(B) * T;
+  CUtensorMap tm_qkv, tm_dy;
+  int rc = get_tensor_map_2d(&tm_qkv, qkv, static_cast<uint64_t>(3) * C, static_cast<uint64_t>(M),
+                             static_cast<uint64_t>(ld), 64, 128);
+  if (rc) return rc;
+  rc = get_tensor_map_2d(&tm_dy, dy, static_cast<uint64_t>(C), static_cast<uint64_t>(M), static_cast<uint64_t>(lddy), 64,
+                         128);
+  if (rc) return rc;
+  {
+    const int warps = 8;
+    attn_delta_kernel<<<static_cast<unsigned>((M + warps - 1) / warps), warps * 32, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(dy), lddy, static_cast<const __nv_bfloat16*>(y), ldy, delta, B, H, T);
+    rc = check_launch("attn_delta");
+    if (rc) return rc;
+  }
+  AttnTcParams p = {};
+  p.B = B; p.H = H; p.T = T;
+  p.scale = scale;
+  p.mask = static_cast<const __nv_bfloat16*>(mask);
+  p.msb = msb; p.msh = msh; p.msq = msq;
+  p.row_lo = mask ? nullptr : row_lo;
+  p.row_hi = mask ? nullptr : row_hi;
+  p.lse = const_cast<float*>(lse);
+  p.delta = delta;
+  p.drop_p = drop_p; p.seed = seed; p.offset = offset;
+  p.dq = static_cast<__nv_bfloat16*>(dqkv);
+  p.dk = p.dq + C;
+  p.dv = p.dq + 2 * C;
+  p.ldd = ldd;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(attn_tc_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDqSmem::BYTES);
+    cudaError_t e2 = cudaFuncSetAttribute(attn_tc_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDkvSmem::BYTES);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      set_last_error("obt_attn_tc_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      return OBT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid((T + ATT_BM - 1) / ATT_BM, H, B);
+  attn_tc_dq_kernel<<<grid, 192, AttnDqSmem::BYTES, stream>>>(tm_qkv, tm_dy, p, C);
+  rc = check_launch("attn_tc_dq");
+  if (rc) return rc;
+  attn_tc_dkv_kernel<<<grid, 192, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_dy, p, C);
+  return check_launch("attn_tc_dkv");
+}

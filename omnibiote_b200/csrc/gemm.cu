@@ -12,57 +12,9 @@
 // forward (K,K), dgrad (K,MN) and wgrad (MN,MN) without materialising transposes.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace obt {
-
-enum : int {
-  EPI_PLAIN = 0,     // D = rb(acc)
-  EPI_RESID = 1,     // D = rb(float(aux_in) + float(rb(acc)))            (residual add / gradient accumulation)
-  EPI_GELU = 2,      // aux_out = U = rb(acc); D = rb(gelu(U))             (model.py:23-25,163-165)
-  EPI_GELU_BWD = 3,  // D = rb(float(rb(acc)) * gelu'(float(aux_in)))      (aux_in = U saved by EPI_GELU)
-  EPI_PARTIAL = 4,   // split-K: fp32 partial tile -> workspace[split]
-  EPI_RESID_DROPOUT = 5,  // D = rb(float(aux_in) + float(rb(rb(acc) * keep/(1-p))))   (resid_dropout, model.py:151,167)
-};
-
-struct GemmParams {
-  int M, N, K;
-  int num_m, num_n, splits, kb_per_split, num_kb;
-  int epi, gelu_mode, vec_ok;
-  __nv_bfloat16* D;
-  long long ldd;
-  const __nv_bfloat16* aux_in;
-  long long ld_aux_in;
-  __nv_bfloat16* aux_out;
-  long long ld_aux_out;
-  float* partial;
-  float drop_p;
-  unsigned long long seed, offset;
-};
-
-constexpr int GEMM_BK = 64;
-constexpr int GEMM_BN = 256;
-constexpr int GEMM_BM_CTA = 128;
-constexpr int GEMM_GROUP_M = 16;
-
-__device__ __forceinline__ float gelu_ref(float x, int mode) {
-  // reference: x * 0.5 * (1.0 + erf(x / 1.41421))  -- the constant is 1.41421, not sqrt(2) (model.py:25)
-  if (mode == 0) return x * 0.5f * (1.0f + erff(x / 1.41421f));
-  // per-primitive bf16 rounding (un-fused TorchScript / CPU eager execution of the same expression)
-  float a = rb(x * 0.5f);
-  float b = rb(x / 1.41421f);
-  float c = rb(erff(b));
-  float d = rb(1.0f + c);
-  return a * d;  // caller rounds
-}
-
-__device__ __forceinline__ float gelu_grad_ref(float x) {
-  const float inv = 1.0f / 1.41421f;
-  float t = x * inv;
-  float cdf = 0.5f * (1.0f + erff(t));
-  // d/dx erf(x/c) = 2/sqrt(pi) * exp(-(x/c)^2) / c
-  float pdf = 0.5f * 1.1283791670955126f * inv * __expf(-t * t);
-  return cdf + x * pdf;
-}
 
 struct TileCoord {
   int m_blk, n_blk, split;
@@ -89,7 +41,7 @@ struct GemmCfg {
   static constexpr int BNL = GEMM_BN / kCG;  // rows of B each CTA loads
   static constexpr uint32_t A_BYTES = GEMM_BM_CTA * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = BNL * GEMM_BK * 2;
-  static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
+  static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 4 * GEMM_STAGE_BYTES_PER_WARP + 1024;
 };
 
 template <int kCG, bool kAMN, bool kBMN>
@@ -109,6 +61,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 256;  // 4 x 4 KB, 128-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -236,103 +189,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    uint8_t* stage = epi_stage + q * GEMM_STAGE_BYTES_PER_WARP;
     int it = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
       const TileCoord tc = tile_coord(tile, p.num_m, p.num_n);
       const int acc_stage = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const long long row = static_cast<long long>(tc.m_blk) * (GEMM_BM_CTA * kCG) + cta_rank * GEMM_BM_CTA + q * 32 + lane;
-      const int n0 = tc.n_blk * GEMM_BN;
-      const bool row_ok = row < p.M;
+      const long long row_base =
+          static_cast<long long>(tc.m_blk) * (GEMM_BM_CTA * kCG) + cta_rank * GEMM_BM_CTA + q * 32;
       mbar_wait(&tfull[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * GEMM_BN;
-#pragma unroll 1
-      for (int c = 0; c < GEMM_BN / 32; ++c) {
-        uint32_t r[32];
-        __syncwarp();  // re-converge after the lane-divergent `continue`s below: tcgen05.ld is .sync.aligned
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (!row_ok || col0 >= p.N) continue;
-        const bool full_chunk = p.vec_ok && (col0 + 32 <= p.N);
-        if (p.epi == EPI_PARTIAL) {
-          float* dst = p.partial + (static_cast<size_t>(tc.split) * p.M + row) * p.N + col0;
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<uint4*>(dst)[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-          } else {
-            for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __uint_as_float(r[j]);
-          }
-          continue;
-        }
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = rb(__uint_as_float(r[j]));
-        if (p.epi == EPI_RESID || p.epi == EPI_GELU_BWD || p.epi == EPI_RESID_DROPOUT) {
-          const __nv_bfloat16* src = p.aux_in + row * p.ld_aux_in + col0;
-          float a[32];
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u = reinterpret_cast<const uint4*>(src)[j];
-              a[8 * j + 0] = bf16_lo(u.x); a[8 * j + 1] = bf16_hi(u.x);
-              a[8 * j + 2] = bf16_lo(u.y); a[8 * j + 3] = bf16_hi(u.y);
-              a[8 * j + 4] = bf16_lo(u.z); a[8 * j + 5] = bf16_hi(u.z);
-              a[8 * j + 6] = bf16_lo(u.w); a[8 * j + 7] = bf16_hi(u.w);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) a[j] = (col0 + j < p.N) ? __bfloat162float(src[j]) : 0.f;
-          }
-          if (p.epi == EPI_RESID) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = a[j] + v[j];
-          } else if (p.epi == EPI_GELU_BWD) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] * gelu_grad_ref(a[j]);
-          } else {
-            // resid dropout: one Philox call per 4 consecutive columns, keyed by the flat element index
-            const float scale = 1.0f / (1.0f - p.drop_p);
-            const unsigned long long base = (static_cast<unsigned long long>(row) * p.N + col0) >> 2;
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              uint4 rnd = philox4x32(p.seed, base + j4, p.offset);
-              const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float u01 = (rr[e] >> 8) * (1.0f / 16777216.0f);
-                float d = (u01 >= p.drop_p) ? rb(v[4 * j4 + e] * scale) : 0.f;
-                v[4 * j4 + e] = a[4 * j4 + e] + d;
-              }
-            }
-          }
-        } else if (p.epi == EPI_GELU) {
-          __nv_bfloat16* udst = p.aux_out + row * p.ld_aux_out + col0;
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              reinterpret_cast<uint4*>(udst)[j] =
-                  make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                             pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-          } else {
-            for (int j = 0; j < 32 && col0 + j < p.N; ++j) udst[j] = __float2bfloat16_rn(v[j]);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_ref(v[j], p.gelu_mode);
-        }
-        __nv_bfloat16* dst = p.D + row * p.ldd + col0;
-        if (full_chunk) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            reinterpret_cast<uint4*>(dst)[j] =
-                make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-        } else {
-          for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
-        }
-      }
+      epilogue_warp_tile(p, taddr, stage, lane, row_base, tc.n_blk * GEMM_BN, tc.split);
       // release this accumulator stage back to the MMA issuer
       tc_fence_before();
       __syncwarp();

@@ -273,7 +273,7 @@ def attention_fwd(qkv: torch.Tensor, B: int, T: int, H: int, d: int, scale: floa
     if impl == "auto":
         dense_ok = mask.tensor is None or (T % 8 == 0 and mask.msq % 8 == 0 and mask.msb % 8 == 0 and mask.msh % 8 == 0
                                            and mask.tensor.data_ptr() % 16 == 0)
-        impl = "tc" if (d == 128 and dense_ok) else "simt"
+        impl = "tc" if (d == 128 and dense_ok and (drop_p == 0.0 or T % 4 == 0)) else "simt"
     if impl == "tc":
         rc = lib.obt_attn_tc_fwd(qkv.data_ptr(), ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
                                  _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0, y.data_ptr(), C,
@@ -299,6 +299,18 @@ def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, se
     q, k, v = qkv.data_ptr(), qkv.data_ptr() + C * esz, qkv.data_ptr() + 2 * C * esz
     dq, dk, dv = dqkv.data_ptr(), dqkv.data_ptr() + C * esz, dqkv.data_ptr() + 2 * C * esz
     use_iv = mask.tensor is None and mask.row_lo is not None
+    if impl == "auto":
+        impl = ATTN_IMPL
+    if impl == "auto":
+        impl = "tc" if (d == 128 and (drop_p == 0.0 or T % 4 == 0)) else "simt"
+    if impl == "tc":
+        rc = _lib.load().obt_attn_tc_bwd(qkv.data_ptr(), ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
+                                         _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0,
+                                         y.data_ptr(), C, dy.data_ptr(), lddy, lse.data_ptr(), delta.data_ptr(),
+                                         dqkv.data_ptr(), 3 * C, B, H, T, d, scale, float(drop_p), seed, offset,
+                                         _stream())
+        _lib.check(rc, "obt_attn_tc_bwd")
+        return dqkv
     rc = _lib.load().obt_attn_simt_bwd(q, k, v, ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
                                        _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0,
                                        y.data_ptr(), C, dy.data_ptr(), lddy, lse.data_ptr(), delta.data_ptr(), dq, dk,

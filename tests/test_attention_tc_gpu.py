@@ -68,3 +68,56 @@ def test_attn_tc_forward(B, T, H, mode):
     tot, tot2 = lse[..., 0] + lse[..., 1], lse2[..., 0] + lse2[..., 1]
     fin = tot2.abs() < 1e6  # rows with a -1e9 row max keep (max, logsum) apart; compare the logsum part there
     assert float((tot[fin] - tot2[fin]).abs().max()) < 2e-2
+
+
+@pytest.mark.parametrize("B,T,H", [(1, 128, 1), (2, 256, 2), (1, 200, 2), (2, 512, 2)])
+@pytest.mark.parametrize("mode", ["none", "interval", "dense"])
+def test_attn_tc_backward(B, T, H, mode):
+    from omnibiote_b200 import ops
+    d = 128
+    C = H * d
+    scale = 8.0 / C
+    torch.manual_seed(7 + B * 1000 + T)
+    qkv = (torch.randn(B * T, 3 * C, device="cuda") * 1.5).to(BF)
+    mask4, spec = None, ops.MaskSpec(None, B, H, T)
+    live = torch.ones(B, T, dtype=torch.bool, device="cuda")
+    if mode != "none":
+        ids = _doc_ids(B, T, T + 1)
+        lo, hi = ops.doc_mask_intervals(ids, 3, True)
+        live = hi > lo  # fully-masked rows never carry gradient in the reference's usage
+        j = torch.arange(T, device="cuda").view(1, 1, T)
+        dense = torch.where((j >= lo.unsqueeze(-1)) & (j < hi.unsqueeze(-1)), 0.0, -1e9).to(BF)
+        mask4 = dense.unsqueeze(1).expand(-1, H, -1, -1)
+        spec = ops.MaskSpec(None, B, H, T, lo, hi) if mode == "interval" else ops.MaskSpec(mask4, B, H, T)
+    y, lse = ops.attention_fwd(qkv, B, T, H, d, scale, spec, 0.0, 0, 0, impl="tc" if (mode != "dense" or T % 8 == 0) else "simt")
+    dy = torch.randn(B * T, C, device="cuda").to(BF)
+    dy = (dy.view(B, T, C) * live.unsqueeze(-1)).reshape(B * T, C).contiguous()
+    qr = qkv.float().requires_grad_(True)
+    _ref(qr, B, T, H, d, scale, mask4).backward(dy.float())
+    dqkv = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, spec, 0.0, 0, 0, impl="tc")
+    torch.cuda.synchronize()
+    for name, sl in [("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))]:
+        err = rel_err(dqkv[:, sl], qr.grad[:, sl])
+        assert err < 1.5e-2, (mode, B, T, H, name, err)
+    dqkv2 = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, spec, 0.0, 0, 0, impl="simt")
+    assert rel_err(dqkv, dqkv2) < 1.5e-2
+
+
+def test_attn_dropout_same_mask_in_both_kernels_and_in_backward():
+    from omnibiote_b200 import ops
+    B, T, H, d = 2, 256, 2, 128
+    C = H * d
+    scale = 8.0 / C
+    torch.manual_seed(3)
+    qkv = (torch.randn(B * T, 3 * C, device="cuda")).to(BF)
+    spec = ops.MaskSpec(None, B, H, T)
+    p, seed, off = 0.25, 99, 8
+    y_tc, lse_tc = ops.attention_fwd(qkv, B, T, H, d, scale, spec, p, seed, off, impl="tc")
+    y_si, lse_si = ops.attention_fwd(qkv, B, T, H, d, scale, spec, p, seed, off, impl="simt")
+    y_nd, _ = ops.attention_fwd(qkv, B, T, H, d, scale, spec, 0.0, 0, 0, impl="tc")
+    assert rel_err(y_tc, y_si) < 1e-2           # identical keep-mask (same Philox indexing) in both kernels
+    assert rel_err(y_tc, y_nd) > 5e-2           # and it really drops something
+    dy = torch.randn(B * T, C, device="cuda").to(BF)
+    g_tc = ops.attention_bwd(qkv, y_tc, dy, lse_tc, B, T, H, d, scale, spec, p, seed, off, impl="tc")
+    g_si = ops.attention_bwd(qkv, y_si, dy, lse_si, B, T, H, d, scale, spec, p, seed, off, impl="simt")
+    assert rel_err(g_tc, g_si) < 2e-2
