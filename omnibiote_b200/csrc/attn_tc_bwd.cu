@@ -270,8 +270,10 @@ struct AttnDkvSmem {
   static constexpr uint32_t DO_OFF = Q_OFF + ATT_TILE_BYTES;
   static constexpr uint32_t PT_OFF = DO_OFF + ATT_TILE_BYTES;
   static constexpr uint32_t DST_OFF = PT_OFF + ATT_TILE_BYTES;
-  static constexpr uint32_t COL_OFF = DST_OFF + ATT_TILE_BYTES;  // per-query (column) parameters: 6 x 128 x 4 B
-  static constexpr uint32_t BAR_OFF = COL_OFF + 6 * 128 * 4;
+  // per-query (column) parameters: float4 {lo, hi, scale*log2e, max*log2e + logsum*log2e}, float2 {delta, scale},
+  // and the 128-key dropout keep bitmask of each query row (4 words)
+  static constexpr uint32_t COL_OFF = DST_OFF + ATT_TILE_BYTES;
+  static constexpr uint32_t BAR_OFF = COL_OFF + 128 * 16 + 128 * 8 + 128 * 16;
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
 
@@ -286,12 +288,9 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint8_t* sDO = smem + AttnDkvSmem::DO_OFF;
   uint8_t* sPT = smem + AttnDkvSmem::PT_OFF;
   uint8_t* sDST = smem + AttnDkvSmem::DST_OFF;
-  int* c_lo = reinterpret_cast<int*>(smem + AttnDkvSmem::COL_OFF);
-  int* c_hi = c_lo + 128;
-  float* c_scale = reinterpret_cast<float*>(c_hi + 128);
-  float* c_off = c_scale + 128;
-  float* c_ls2 = c_off + 128;
-  float* c_dl = c_ls2 + 128;
+  float4* c_a = reinterpret_cast<float4*>(smem + AttnDkvSmem::COL_OFF);
+  float2* c_b = reinterpret_cast<float2*>(c_a + 128);
+  uint4* c_keep = reinterpret_cast<uint4*>(c_b + 128);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnDkvSmem::BAR_OFF);
   uint64_t* kv_full = bars + 0;
   uint64_t* qdo_full = bars + 1;
@@ -393,13 +392,14 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     for (int it = 0; it < nq; ++it) {
       if (!((rel >> it) & 1ull)) continue;
       const int i0 = it * ATT_BM;
-      // per-query parameters of this tile (thread r loads query i0 + r)
+      // per-query parameters of this tile (thread r loads query i0 + r) + dropout keep bits of its 128 keys
       compute_bar_sync();
       {
         const int i = i0 + r;
-        int lo = 0, hi = T;
+        int lo = 0, hi = 0;  // query beyond the sequence: contributes nothing
         float sc = p.scale, off = 0.f, ls2 = 0.f, dl = 0.f;
         if (i < T) {
+          lo = 0; hi = T;
           if (p.row_lo != nullptr) {
             lo = p.row_lo[static_cast<long long>(b) * T + i];
             hi = p.row_hi[static_cast<long long>(b) * T + i];
@@ -408,15 +408,32 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           off = p.lse[2 * (bh * T + i)];
           ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
           dl = p.delta[bh * T + i];
-        } else {
-          lo = 0; hi = 0;  // query beyond the sequence: contributes nothing
         }
-        c_lo[r] = lo; c_hi[r] = hi; c_scale[r] = sc; c_off[r] = off; c_ls2[r] = ls2; c_dl[r] = dl;
+        c_a[r] = make_float4(__int_as_float(lo), __int_as_float(hi), sc * LOG2E, off * LOG2E + ls2);
+        c_b[r] = make_float2(dl, sc);
+        if (use_drop) {
+          uint32_t bits[4] = {0u, 0u, 0u, 0u};
+          if (i < T) {
+            const unsigned long long e0 = (static_cast<unsigned long long>(bh) * T + i) * T + static_cast<unsigned long long>(j0);
+#pragma unroll 4
+            for (int g = 0; g < 32; ++g) {
+              const uint4 rnd = philox4x32(p.seed, (e0 >> 2) + g, p.offset);
+              uint32_t nib = 0;
+              nib |= ((rnd.x >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 1u : 0u;
+              nib |= ((rnd.y >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 2u : 0u;
+              nib |= ((rnd.z >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 4u : 0u;
+              nib |= ((rnd.w >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 8u : 0u;
+              bits[g >> 3] |= nib << ((g & 7) * 4);
+            }
+          }
+          c_keep[r] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+        }
       }
       compute_bar_sync();
       mbar_wait(sdp_full, n & 1);
       tc_fence_after();
       if (n > 0) mbar_wait(qdo_empty, (n - 1) & 1);  // previous P^T / dS^T tiles fully consumed
+      const float keep_scale = use_drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t sv[32], dv[32];
@@ -429,27 +446,26 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         for (int e = 0; e < 32; ++e) {
           const int col = c * 32 + e;
           const int i = i0 + col;
-          const float sc = c_scale[col];
-          float sp;
-          bool vis;
+          const float4 ca = c_a[col];
+          const float2 cb = c_b[col];
+          float pr;
           if (p.mask != nullptr) {
-            vis = key_ok && i < T;
+            const bool vis = key_ok && i < T;
             const float bias = vis ? __bfloat162float(p.mask[b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq + j]) : 0.f;
-            sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
+            const float sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
+            pr = vis ? fast_exp2(sp * LOG2E - ca.w) : 0.f;
           } else {
-            vis = key_ok && j >= c_lo[col] && j < c_hi[col];
-            sp = __uint_as_float(sv[e]) * sc;
+            const bool vis = key_ok && j >= __float_as_int(ca.x) && j < __float_as_int(ca.y);
+            pr = vis ? fast_exp2(__uint_as_float(sv[e]) * ca.z - ca.w) : 0.f;
           }
-          const float pr = vis ? fast_exp2((sp - c_off[col]) * LOG2E - c_ls2[col]) : 0.f;
           float ks = 1.0f;
-          if (use_drop && vis) {
-            const unsigned long long eidx = (static_cast<unsigned long long>(bh) * T + i) * T + j;
-            const uint4 rnd = philox4x32(p.seed, eidx >> 2, p.offset);
-            const uint32_t w = (eidx & 3) == 0 ? rnd.x : (eidx & 3) == 1 ? rnd.y : (eidx & 3) == 2 ? rnd.z : rnd.w;
-            ks = ((w >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 1.0f / (1.0f - p.drop_p) : 0.f;
+          if (use_drop) {
+            const uint4 kb = c_keep[col];
+            const uint32_t word = q == 0 ? kb.x : q == 1 ? kb.y : q == 2 ? kb.z : kb.w;
+            ks = ((word >> lane) & 1u) ? keep_scale : 0.f;
           }
           pt[e] = pr * ks;
-          dst[e] = pr * (__uint_as_float(dv[e]) * ks - c_dl[col]) * sc;
+          dst[e] = pr * (__uint_as_float(dv[e]) * ks - cb.x) * cb.y;
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {

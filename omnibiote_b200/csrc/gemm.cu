@@ -257,10 +257,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     attr_set = true;
   }
   const int total_tiles = p.num_m * p.num_n * p.splits;
-  const int max_clusters = sm_count() / kCG;
-  const int clusters = total_tiles < max_clusters ? total_tiles : max_clusters;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(clusters * kCG);
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
@@ -271,6 +268,22 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // Persistent grid = number of CTAs (clusters) that can be CO-RESIDENT. For CTA pairs this can be fewer than
+  // SMs/2 (a GPC with an odd number of enabled SMs strands one): launching more would run a second wave and
+  // double the kernel time (first cta_group::2 measurements, profiles/r01_*).
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    int n = sm_count() / kCG;
+    if (kCG > 1) {
+      cfg.gridDim = dim3(sm_count() / kCG * kCG);
+      int q = 0;
+      if (cudaOccupancyMaxActiveClusters(&q, kern, &cfg) == cudaSuccess && q > 0 && q < n) n = q;
+      (void)cudaGetLastError();
+    }
+    max_clusters = n;
+  }
+  const int clusters = total_tiles < max_clusters ? total_tiles : max_clusters;
+  cfg.gridDim = dim3(clusters * kCG);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
   if (e != cudaSuccess) {
     set_last_error("gemm launch: %s", cudaGetErrorString(e));
@@ -310,7 +323,9 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   if (epilogue == EPI_GELU) OBT_REQUIRE(aux_out != nullptr, "obt_gemm_bf16: GELU epilogue needs aux_out");
 
   int cg = g_force_cta_group;
-  if (cg == 0) cg = (M > 128) ? 2 : 1;
+  // auto: one CTA per SM with 128x256 tiles measured 1.17-1.40 PFLOP/s on the block/head shapes (86-95 % of cuBLAS);
+  // the CTA-pair variant stays selectable for ablations (obt_gemm_set_cta_group).
+  if (cg == 0) cg = 1;
   const int bm = GEMM_BM_CTA * cg;
 
   GemmParams p = {};

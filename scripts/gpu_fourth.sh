@@ -1,0 +1,18 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout -k 10 600 python -m pytest tests/test_attention_tc_gpu.py tests/test_gemm_gpu.py -q -m gpu -p no:cacheprovider --tb=short > gpurun_out/t4.log 2>&1
+echo "tests exit $?"; tail -n 5 gpurun_out/t4.log
+L=gpurun_out/probe4.log; : > $L
+run() { echo "--- $*" >> $L; timeout -k 5 120 python scripts/gemm_probe.py "$@" >> $L 2>&1; echo "exit $?" >> $L; }
+run 2 0 0 32768 4096 1024 t
+run 2 0 0 32768 1024 4096 t
+run 2 1 1 4096 1024 32768 t
+run 1 1 1 1024 1024 32768 t
+run 1 0 1 32768 1024 65536 t
+grep -E "^---|time|cuBLAS|bad=" $L
+timeout -k 10 1200 python bench.py --steps 2 --warmup 3 --skip-cpu-baseline > gpurun_out/bench_full4.log 2>&1; echo "bench exit $?"; tail -n 1 gpurun_out/bench_full4.log
+timeout -k 10 1200 python bench.py --steps 2 --warmup 3 --dropout 0.0 --skip-cpu-baseline > gpurun_out/bench_full4_nodrop.log 2>&1; echo "bench exit $?"; tail -n 1 gpurun_out/bench_full4_nodrop.log
+timeout -k 10 600 python bench.py --steps 1 --warmup 3 --global-batch 32 --skip-cpu-baseline > gpurun_out/bench_plain.log 2>&1 &&
+timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches4.csv python bench.py --steps 1 --warmup 3 --global-batch 32 --skip-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+echo "ncu launches exit $?"
