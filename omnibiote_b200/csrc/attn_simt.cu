@@ -71,7 +71,7 @@ __device__ __forceinline__ float mask_bias(const AttnSimtParams& p, int b, int h
 __device__ __forceinline__ float keep_scale(const AttnSimtParams& p, int b, int h, int i, int j) {
   if (p.drop_p <= 0.f) return 1.0f;
   const unsigned long long e = ((static_cast<unsigned long long>(b) * p.H + h) * p.T + i) * p.T + j;
-  uint4 r = philox4x32(p.seed, e >> 2, p.offset);
+  uint4 r = rand4x32(p.seed, e >> 2, p.offset);
   const uint32_t w = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
   return ((w >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 1.0f / (1.0f - p.drop_p) : 0.f;
 }

@@ -273,7 +273,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
           const float ks = 1.0f / (1.0f - p.drop_p);
 #pragma unroll
           for (int g4 = 0; g4 < 8; ++g4) {
-            const uint4 rnd = philox4x32(p.seed, (e0 >> 2) + g4, p.offset);
+            const uint4 rnd = rand4x32(p.seed, (e0 >> 2) + g4, p.offset);
             const uint32_t w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e)

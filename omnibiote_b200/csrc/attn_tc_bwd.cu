@@ -417,7 +417,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             const unsigned long long e0 = (static_cast<unsigned long long>(bh) * T + i) * T + static_cast<unsigned long long>(j0);
 #pragma unroll 4
             for (int g = 0; g < 32; ++g) {
-              const uint4 rnd = philox4x32(p.seed, (e0 >> 2) + g, p.offset);
+              const uint4 rnd = rand4x32(p.seed, (e0 >> 2) + g, p.offset);
               uint32_t nib = 0;
               nib |= ((rnd.x >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 1u : 0u;
               nib |= ((rnd.y >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 2u : 0u;

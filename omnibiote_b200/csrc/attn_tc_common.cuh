@@ -64,7 +64,7 @@ __device__ __forceinline__ void issue_128x128x128(uint32_t d_tmem, uint32_t a_ad
 
 // dropout keep * 1/(1-p) factors for 4 consecutive keys starting at flat element index e0 (e0 % 4 == 0)
 __device__ __forceinline__ void keep4(const AttnTcParams& p, unsigned long long e0, float (&ks)[4]) {
-  const uint4 rnd = philox4x32(p.seed, e0 >> 2, p.offset);
+  const uint4 rnd = rand4x32(p.seed, e0 >> 2, p.offset);
   const float s = 1.0f / (1.0f - p.drop_p);
   ks[0] = ((rnd.x >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? s : 0.f;
   ks[1] = ((rnd.y >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? s : 0.f;

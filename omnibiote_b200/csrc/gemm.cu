@@ -41,11 +41,12 @@ struct GemmCfg {
   static constexpr int BNL = GEMM_BN / kCG;  // rows of B each CTA loads
   static constexpr uint32_t A_BYTES = GEMM_BM_CTA * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = BNL * GEMM_BK * 2;
-  static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 4 * GEMM_STAGE_BYTES_PER_WARP + 1024;
+  static constexpr uint32_t SMEM_BYTES =
+      STAGES * (A_BYTES + B_BYTES) + 256 + GEMM_EPI_WARPS * GEMM_STAGE_BYTES_PER_WARP + 1024;
 };
 
 template <int kCG, bool kAMN, bool kBMN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<kCG>;
   constexpr int STAGES = Cfg::STAGES;
@@ -79,7 +80,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4 * kCG);
+      mbar_init(&tempty[i], GEMM_EPI_WARPS * kCG);
     }
     fence_barrier_init();
   }
@@ -188,8 +189,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    uint8_t* stage = epi_stage + q * GEMM_STAGE_BYTES_PER_WARP;
+    // 8 epilogue warps: two per TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31); the pair splits
+    // the 256 accumulator columns in halves, which keeps the GELU / dropout epilogues shorter than the main loop.
+    const int q = warp & 3;
+    const int ew = warp - 2;       // 0..7
+    const int chalf = ew >> 2;     // which 128-column half this warp stores
+    uint8_t* stage = epi_stage + ew * GEMM_STAGE_BYTES_PER_WARP;
     int it = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
       const TileCoord tc = tile_coord(tile, p.num_m, p.num_n);
@@ -200,7 +205,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tfull[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * GEMM_BN;
-      epilogue_warp_tile(p, taddr, stage, lane, row_base, tc.n_blk * GEMM_BN, tc.split);
+      epilogue_warp_tile(p, taddr, stage, lane, row_base, tc.n_blk * GEMM_BN, tc.split, chalf * 2, chalf * 2 + 2);
       // release this accumulator stage back to the MMA issuer
       tc_fence_before();
       __syncwarp();
@@ -258,7 +263,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int total_tiles = p.num_m * p.num_n * p.splits;
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

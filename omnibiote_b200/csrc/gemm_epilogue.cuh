@@ -40,10 +40,31 @@ constexpr int GEMM_BN = 256;
 constexpr int GEMM_BM_CTA = 128;
 constexpr int GEMM_GROUP_M = 16;
 constexpr uint32_t GEMM_STAGE_BYTES_PER_WARP = 32 * 128;  // epilogue staging: 32 rows x 128 B
+constexpr int GEMM_EPI_WARPS = 8;                          // two per TMEM lane quadrant
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;     // warp 0 = TMA, warp 1 = MMA, warps 2.. = epilogue
+
+// 1 + erf(t) and exp(-t^2) in ~14 instructions (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7, no cancellation on the
+// negative side). libdevice erff costs ~40 instructions and made the GELU epilogues 5-8x longer than the main loop
+// (profiles/r01_launches_v1.txt); the result is rounded to bf16 (2^-9 relative) right after.
+__device__ __forceinline__ void one_plus_erf(float t, float& cdf2, float& e) {
+  const float a = fabsf(t);
+  const float k = __frcp_rn(fmaf(0.3275911f, a, 1.0f));
+  e = __expf(-a * a);
+  float poly = fmaf(1.061405429f, k, -1.453152027f);
+  poly = fmaf(poly, k, 1.421413741f);
+  poly = fmaf(poly, k, -0.284496736f);
+  poly = fmaf(poly, k, 0.254829592f);
+  const float pe = poly * k * e;        // = 1 - erf(|t|)
+  cdf2 = (t >= 0.f) ? 2.0f - pe : pe;   // = 1 + erf(t)
+}
 
 __device__ __forceinline__ float gelu_ref(float x, int mode) {
   // reference: x * 0.5 * (1.0 + erf(x / 1.41421))  -- the constant is 1.41421, not sqrt(2) (model.py:25)
-  if (mode == 0) return x * 0.5f * (1.0f + erff(x / 1.41421f));
+  if (mode == 0) {
+    float cdf2, e;
+    one_plus_erf(x * (1.0f / 1.41421f), cdf2, e);
+    return x * 0.5f * cdf2;
+  }
   // per-primitive bf16 rounding (un-fused TorchScript / CPU eager execution of the same expression)
   float a = rb(x * 0.5f);
   float b = rb(x / 1.41421f);
@@ -54,11 +75,10 @@ __device__ __forceinline__ float gelu_ref(float x, int mode) {
 
 __device__ __forceinline__ float gelu_grad_ref(float x) {
   const float inv = 1.0f / 1.41421f;
-  float t = x * inv;
-  float cdf = 0.5f * (1.0f + erff(t));
-  // d/dx erf(x/c) = 2/sqrt(pi) * exp(-(x/c)^2) / c
-  float pdf = 0.5f * 1.1283791670955126f * inv * __expf(-t * t);
-  return cdf + x * pdf;
+  float cdf2, e;
+  one_plus_erf(x * inv, cdf2, e);
+  // d/dx [x * 0.5 * (1 + erf(x/c))] = 0.5 (1 + erf(x/c)) + x * 0.5 * 2/sqrt(pi) * exp(-(x/c)^2) / c
+  return 0.5f * cdf2 + x * (0.5f * 1.1283791670955126f * inv) * e;
 }
 
 __device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
@@ -106,7 +126,7 @@ __device__ __forceinline__ void epilogue_segment(const GemmParams& p, float (&v)
       const unsigned long long base = (static_cast<unsigned long long>(grow) * p.N + gcol) >> 2;
 #pragma unroll
       for (int j4 = 0; j4 < 2; ++j4) {
-        const uint4 rnd = philox4x32(p.seed, base + j4, p.offset);
+        const uint4 rnd = rand4x32(p.seed, base + j4, p.offset);
         const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -178,10 +198,10 @@ __device__ __forceinline__ void partial_readback(const GemmParams& p, const uint
 // Whole 128 x 256 accumulator slice of one epilogue warp: rows row_base..row_base+31 (TMEM lanes of this warp's
 // quadrant), columns n0..n0+255.
 __device__ __forceinline__ void epilogue_warp_tile(const GemmParams& p, uint32_t taddr, uint8_t* stage, int lane,
-                                                   long long row_base, int n0, int split) {
+                                                   long long row_base, int n0, int split, int c_begin, int c_end) {
   const int rsub = lane >> 3, seg = lane & 7;
 #pragma unroll 1
-  for (int c = 0; c < GEMM_BN / 64; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     const int col_base = n0 + c * 64;
     if (col_base >= p.N) break;  // warp-uniform
     uint32_t r0[32], r1[32];

@@ -305,4 +305,17 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t subseq, uint
   return make_uint4(c0, c1, c2, c3);
 }
 
+// Cheap counter RNG for dropout masks: one splitmix64 hash of (seed, offset, counter) -> 4 x 16 random bits, each
+// widened to the top half of a 32-bit word so call sites can treat the result like four 32-bit uniforms.
+// (Philox4x32-10 above costs ~100 dependent integer ops per call; with one softmax warp per scheduler that latency
+// dominated the attention kernels. The reference's dropout stream is torch's own, so parity is statistical anyway.)
+__device__ __forceinline__ uint4 rand4x32(uint64_t seed, uint64_t ctr, uint64_t offset) {
+  uint64_t z = ctr * 0x9E3779B97F4A7C15ull + (seed ^ (offset * 0xD1B54A32D192ED03ull));
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const uint32_t lo = static_cast<uint32_t>(z), hi = static_cast<uint32_t>(z >> 32);
+  return make_uint4(lo << 16, lo & 0xFFFF0000u, hi << 16, hi & 0xFFFF0000u);
+}
+
 }  // namespace obt

@@ -28,7 +28,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // keep/scale decision for element `e` of a flat tensor; 4 consecutive elements share one Philox call.
 __device__ __forceinline__ void dropout4(unsigned long long seed, unsigned long long offset, unsigned long long e4,
                                          float p, bool (&keep)[4]) {
-  uint4 r = philox4x32(seed, e4, offset);
+  uint4 r = rand4x32(seed, e4, offset);
   keep[0] = (r.x >> 8) * (1.0f / 16777216.0f) >= p;
   keep[1] = (r.y >> 8) * (1.0f / 16777216.0f) >= p;
   keep[2] = (r.z >> 8) * (1.0f / 16777216.0f) >= p;
@@ -288,13 +288,23 @@ __global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_b
 // dgamma[c] = rb( (accumulate ? dgamma[c] : 0) + rb(sum_b partial[b][c]) )
 __global__ void ln_dgamma_reduce_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ dgamma, int nblk,
                                         int C, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  // block (32, 8): 32 columns x 8 row groups; coalesced 128-byte reads per row
+  __shared__ float s[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int ry = threadIdx.y;
   float t = 0.f;
-  for (int b = 0; b < nblk; ++b) t += partial[static_cast<long long>(b) * C + c];
-  float o = rb(t);
-  if (accumulate) o += __bfloat162float(dgamma[c]);
-  dgamma[c] = __float2bfloat16_rn(o);
+  if (c < C)
+    for (int b = ry; b < nblk; b += 8) t += partial[static_cast<long long>(b) * C + c];
+  s[ry][threadIdx.x] = t;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += s[k][threadIdx.x];
+    float o = rb(tot);
+    if (accumulate) o += __bfloat162float(dgamma[c]);
+    dgamma[c] = __float2bfloat16_rn(o);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -507,15 +517,15 @@ extern "C" int obt_layernorm_fwd(const void* x, const void* gamma, void* y, void
 }
 
 // workspace: fp32 [obt_layernorm_bwd_workspace_rows() * C]
-extern "C" int obt_layernorm_bwd_workspace_rows(void) { return sm_count() * 2; }
+extern "C" int obt_layernorm_bwd_workspace_rows(void) { return sm_count() * 4; }
 
 extern "C" int obt_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
                                  const void* dres, void* dx, void* dgamma, int accumulate_dgamma, float* workspace,
                                  long long M, int C, float dy_div, cudaStream_t stream) {
   OBT_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && workspace, "obt_layernorm_bwd: null pointer");
   OBT_REQUIRE(C % 8 == 0 && C <= 2048, "obt_layernorm_bwd: C=%d must be a multiple of 8 and <= 2048", C);
-  const int wpb = 4;
-  int grid = sm_count() * 2;
+  const int wpb = (C <= 1024) ? 8 : 4;  // 32 KB of dgamma staging per block either way
+  int grid = sm_count() * 4;
   if (M < static_cast<long long>(grid) * wpb) grid = static_cast<int>((M + wpb - 1) / wpb);
   if (grid < 1) grid = 1;
   const size_t smem = static_cast<size_t>(wpb) * C * sizeof(float);
@@ -530,8 +540,8 @@ extern "C" int obt_layernorm_bwd(const void* dy, const void* x, const void* gamm
     ln_bwd_kernel<8><<<grid, wpb * 32, smem, stream>>>(a, b, g, mean, rstd, r, o, workspace, M, C, dy_div);
   int rc = check_launch("ln_bwd");
   if (rc) return rc;
-  ln_dgamma_reduce_kernel<<<(C + 127) / 128, 128, 0, stream>>>(workspace, static_cast<__nv_bfloat16*>(dgamma), grid, C,
-                                                               accumulate_dgamma);
+  ln_dgamma_reduce_kernel<<<(C + 31) / 32, dim3(32, 8), 0, stream>>>(workspace, static_cast<__nv_bfloat16*>(dgamma),
+                                                                     grid, C, accumulate_dgamma);
   return check_launch("ln_dgamma_reduce");
 }
 
