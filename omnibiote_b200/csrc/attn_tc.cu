@@ -5,11 +5,14 @@
 // (training/model.py:111-148): q,k,v are read in place from the fused qkv buffer [M, 3C] (no transposes), y is
 // written head-major into [M, C].
 //
-// One CTA per (128-query tile, head, batch); 6 warps:
+// One CTA per (128-query tile, head, batch); 10 warps:
 //   warp 0     TMA producer: Q once, then K_j / V_j tiles through 2-stage rings
 //   warp 1     MMA issuer  : S_{j+1} = Q K_{j+1}^T is issued before O += P_j V_j so it overlaps softmax(j)
-//   warps 2-5  softmax     : one thread per query row (TMEM lane), S read with tcgen05.ld, P written as bf16 into a
-//                            128B-swizzled smem tile (A operand of the PV MMA), O rescaled in TMEM when the max moves
+//   warps 2-9  softmax     : TWO threads per query row (TMEM lane): warps 2-5 own key columns 0..63 of every S tile
+//                            and O columns 0..63, warps 6-9 the other halves; the pair exchanges its half-row maxima
+//                            through smem (one 256-thread named barrier per tile). S is read with tcgen05.ld, P is
+//                            written as bf16 into a 128B-swizzled smem tile (A operand of the PV MMA), O is rescaled
+//                            in TMEM only when the running max moved.
 // TMEM: S ping-pong (2 x 128 columns) + O (128 columns).
 // Mask modes: none | per-row visible key interval [lo,hi) (document / padding masks; KV tiles outside the union of
 // the tile's intervals are skipped) | dense additive bf16 bias (arbitrary masks). Fully-masked rows (finite -1e9 on
@@ -23,11 +26,14 @@ struct AttnFwdSmem {
   static constexpr uint32_t K_OFF = Q_OFF + ATT_TILE_BYTES;          // 2 stages
   static constexpr uint32_t V_OFF = K_OFF + 2 * ATT_TILE_BYTES;      // 2 stages
   static constexpr uint32_t P_OFF = V_OFF + 2 * ATT_TILE_BYTES;
-  static constexpr uint32_t BAR_OFF = P_OFF + ATT_TILE_BYTES;
+  static constexpr uint32_t X_OFF = P_OFF + ATT_TILE_BYTES;          // half-row exchange: float [2 buffers][2 halves][128]
+  static constexpr uint32_t BAR_OFF = X_OFF + 2 * 2 * 128 * 4;
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
 
-__global__ void __launch_bounds__(192, 1)
+constexpr int ATT_THREADS = 64 + 256;  // TMA warp, MMA warp, 8 compute warps
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParams p, int C) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -35,6 +41,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
   uint8_t* sK = smem + AttnFwdSmem::K_OFF;
   uint8_t* sV = smem + AttnFwdSmem::V_OFF;
   uint8_t* sP = smem + AttnFwdSmem::P_OFF;
+  float* sX = reinterpret_cast<float*>(smem + AttnFwdSmem::X_OFF);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnFwdSmem::BAR_OFF);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [2]
@@ -62,9 +69,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+      mbar_init(&s_empty[i], 8);
     }
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
     fence_barrier_init();
     s_range[0] = T;
@@ -150,10 +157,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
       }
     }
   } else {
-    // ===================== softmax / correction / epilogue (thread = query row) =====================
-    const int q = warp & 3;
-    const int r = q * 32 + lane;  // row within the tile == TMEM lane
-    const int i = t0 + r;         // query position
+    // ===================== softmax / correction / epilogue (two threads per query row) =====================
+    const int q = warp & 3;              // TMEM lane quadrant
+    const int half = (warp - 2) >> 2;    // which 64 key columns of S / 64 columns of O this thread owns
+    const int r = q * 32 + lane;         // row within the tile == TMEM lane
+    const int i = t0 + r;                // query position
     const bool row_ok = i < T;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     int lo = 0, hi = T;
@@ -170,7 +178,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     const __nv_bfloat16* mrow =
         (p.mask != nullptr && row_ok) ? p.mask + b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq : nullptr;
     const bool use_drop = p.drop_p > 0.f;
-    float m_run = -INFINITY, l_run = 0.f;  // running max (log2 domain) and exp-sum
+    float m_run = -INFINITY, l_run = 0.f;  // running max (log2 domain, whole row) and exp-sum (this half only)
 
     for (int jj = 0; jj < n_tiles; ++jj) {
       const int st = jj & 1;
@@ -178,10 +186,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
       mbar_wait(&s_full[st], (jj >> 1) & 1);
       tc_fence_after();
       const uint32_t s_addr = lane_addr + st * 128;
-      // ---- pass 1: row max of the scaled + biased scores of this tile
+      // ---- pass 1: max of the scaled + biased scores of this thread's 64 columns
       float tmax = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t v[32];
         __syncwarp();
         tmem_ld_32x32(s_addr + c * 32, v);
@@ -211,16 +220,22 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
           }
         }
       }
+      // exchange the half-row maxima with the partner thread (same row, other column half)
+      float* xbuf = sX + (jj & 1) * 256;
+      xbuf[half * 128 + r] = tmax;
+      compute_bar_sync256();
+      tmax = fmaxf(tmax, xbuf[(half ^ 1) * 128 + r]);
       const float m_new = fmaxf(m_run, tmax);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = fast_exp2(m_run - m_use);  // m_run = -inf -> 0
-      // ---- wait for O += P_{j-1} V_{j-1}; rescale O when the running max moved
+      // ---- wait for O += P_{j-1} V_{j-1}; rescale this thread's 64 O columns when the running max moved
       if (jj > 0) {
         mbar_wait(pv_done, (jj - 1) & 1);
         tc_fence_after();
         if (__any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = half * 2 + cc;
             uint32_t o[32];
             __syncwarp();
             tmem_ld_32x32(lane_addr + 256 + c * 32, o);
@@ -232,10 +247,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
           tmem_st_wait();
         }
       }
-      // ---- pass 2: P = exp2(s - m), row sum, bf16 P tile into swizzled smem
+      // ---- pass 2: P = exp2(s - m), partial row sum, bf16 P into swizzled smem
       float lsum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t v[32];
         __syncwarp();
         tmem_ld_32x32(s_addr + c * 32, v);
@@ -266,18 +282,16 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
 #pragma unroll
         for (int e = 0; e < 32; ++e) lsum += pr[e];
         if (use_drop && row_ok) {
-          // one Philox call per 4 consecutive keys; element index e = ((b*H+h)*T + i)*T + j as in the generic kernel.
-          // (needs T % 4 == 0 so that groups of 4 keys never straddle rows; enforced by the host wrapper)
+          // one RNG call per 4 consecutive keys; element index e = ((b*H+h)*T + i)*T + j as in the generic kernel
+          // (T % 4 == 0 so that groups of 4 keys never straddle rows; enforced by the host wrapper)
           const unsigned long long e0 =
               ((static_cast<unsigned long long>(b) * p.H + h) * T + i) * T + static_cast<unsigned long long>(j0 + c * 32);
-          const float ks = 1.0f / (1.0f - p.drop_p);
 #pragma unroll
           for (int g4 = 0; g4 < 8; ++g4) {
-            const uint4 rnd = rand4x32(p.seed, (e0 >> 2) + g4, p.offset);
-            const uint32_t w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+            float ks[4];
+            keep4(p, e0 + 4 * g4, ks);
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              pr[g4 * 4 + e] *= ((w[e] >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? ks : 0.f;
+            for (int e = 0; e < 4; ++e) pr[g4 * 4 + e] *= ks[e];
           }
         }
 #pragma unroll
@@ -298,13 +312,18 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         mbar_arrive(&s_empty[st]);
       }
     }
-    // ---- epilogue: O / l -> y, (max, log-sum) -> lse
+    // ---- epilogue: total row sum = both halves; O / l -> y (this thread's 64 columns), (max, log-sum) -> lse
+    float* xbuf = sX + (n_tiles & 1) * 256;
+    xbuf[half * 128 + r] = l_run;
+    compute_bar_sync256();
+    const float l_tot = l_run + xbuf[(half ^ 1) * 128 + r];
     mbar_wait(pv_done, (n_tiles - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.0f / l_run;
+    const float inv_l = 1.0f / l_tot;
     __nv_bfloat16* yrow = p.y + (static_cast<long long>(row0) + i) * p.ldy + h * ATT_D;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = half * 2 + cc;
       uint32_t o[32];
       __syncwarp();
       tmem_ld_32x32(lane_addr + 256 + c * 32, o);
@@ -320,10 +339,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         }
       }
     }
-    if (row_ok && p.lse != nullptr) {
+    if (row_ok && half == 0 && p.lse != nullptr) {
       float* l = p.lse + 2 * ((static_cast<long long>(b) * p.H + h) * T + i);
       l[0] = m_run / LOG2E;
-      l[1] = logf(l_run);
+      l[1] = logf(l_tot);
     }
     tc_fence_before();
   }
@@ -379,6 +398,6 @@ extern "C" int obt_attn_tc_fwd(const void* qkv, long long ld, const void* mask, 
     attr_set = true;
   }
   dim3 grid((T + ATT_BM - 1) / ATT_BM, H, B);
-  attn_tc_fwd_kernel<<<grid, 192, AttnFwdSmem::BYTES, stream>>>(tm, p, C);
+  attn_tc_fwd_kernel<<<grid, ATT_THREADS, AttnFwdSmem::BYTES, stream>>>(tm, p, C);
   return check_launch("attn_tc_fwd");
 }

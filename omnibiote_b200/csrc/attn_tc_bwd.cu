@@ -47,7 +47,7 @@ struct AttnDqSmem {
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(ATT_THREADS_BWD, 1)
 attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dy,
                   const AttnTcParams p, int C) {
   extern __shared__ uint8_t smem_raw[];
@@ -85,7 +85,7 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(ds_full, 4);
+    mbar_init(ds_full, ATT_COMPUTE_WARPS);
     mbar_init(dq_done, 1);
     fence_barrier_init();
     s_range[0] = T;
@@ -162,6 +162,7 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;  // two threads per query row: key columns / dQ columns [64*half, 64*half+64)
     const int r = q * 32 + lane;
     const int i = t0 + r;
     const bool row_ok = i < T;
@@ -190,7 +191,8 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
       tc_fence_after();
       if (jj > 0) mbar_wait(dq_done, (jj - 1) & 1);  // previous dS tile fully consumed
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t sv[32], dv[32];
         __syncwarp();
         tmem_ld_32x32(lane_addr + c * 32, sv);
@@ -236,7 +238,8 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
     tc_fence_after();
     __nv_bfloat16* drow = p.dq + (static_cast<long long>(row0) + i) * p.ldd + h * ATT_D;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = half * 2 + cc;
       uint32_t o[32];
       __syncwarp();
       tmem_ld_32x32(lane_addr + 256 + c * 32, o);
@@ -277,7 +280,7 @@ struct AttnDkvSmem {
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(ATT_THREADS_BWD, 1)
 attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dy,
                    const AttnTcParams p, int C) {
   extern __shared__ uint8_t smem_raw[];
@@ -313,7 +316,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     mbar_init(qdo_full, 1);
     mbar_init(qdo_empty, 1);
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 4);
+    mbar_init(pds_full, ATT_COMPUTE_WARPS);
     fence_barrier_init();
     s_rel[0] = 0;
     s_rel[1] = 0;
@@ -382,6 +385,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;  // two threads per key row: query columns [64*half, +64); dV (0) / dK (1) epilogue
     const int r = q * 32 + lane;  // key row within the tile
     const int j = j0 + r;
     const bool key_ok = j < T;
@@ -393,7 +397,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       if (!((rel >> it) & 1ull)) continue;
       const int i0 = it * ATT_BM;
       // per-query parameters of this tile (thread r loads query i0 + r) + dropout keep bits of its 128 keys
-      compute_bar_sync();
+      compute_bar_sync256();
       {
         const int i = i0 + r;
         int lo = 0, hi = 0;  // query beyond the sequence: contributes nothing
@@ -409,15 +413,18 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
           dl = p.delta[bh * T + i];
         }
-        c_a[r] = make_float4(__int_as_float(lo), __int_as_float(hi), sc * LOG2E, off * LOG2E + ls2);
-        c_b[r] = make_float2(dl, sc);
+        if (half == 0) {
+          c_a[r] = make_float4(__int_as_float(lo), __int_as_float(hi), sc * LOG2E, off * LOG2E + ls2);
+          c_b[r] = make_float2(dl, sc);
+        }
         if (use_drop) {
-          uint32_t bits[4] = {0u, 0u, 0u, 0u};
+          // this thread generates the keep bits of keys [64*half, 64*half+64) of query row i0 + r
+          uint32_t bits[2] = {0u, 0u};
           if (i < T) {
             const unsigned long long e0 = (static_cast<unsigned long long>(bh) * T + i) * T + static_cast<unsigned long long>(j0);
 #pragma unroll 4
-            for (int g = 0; g < 32; ++g) {
-              const uint4 rnd = rand4x32(p.seed, (e0 >> 2) + g, p.offset);
+            for (int g = 0; g < 16; ++g) {
+              const uint4 rnd = rand4x32(p.seed, (e0 >> 2) + half * 16 + g, p.offset);
               uint32_t nib = 0;
               nib |= ((rnd.x >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 1u : 0u;
               nib |= ((rnd.y >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 2u : 0u;
@@ -426,16 +433,17 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
               bits[g >> 3] |= nib << ((g & 7) * 4);
             }
           }
-          c_keep[r] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+          reinterpret_cast<uint2*>(c_keep + r)[half] = make_uint2(bits[0], bits[1]);
         }
       }
-      compute_bar_sync();
+      compute_bar_sync256();
       mbar_wait(sdp_full, n & 1);
       tc_fence_after();
       if (n > 0) mbar_wait(qdo_empty, (n - 1) & 1);  // previous P^T / dS^T tiles fully consumed
       const float keep_scale = use_drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t sv[32], dv[32];
         __syncwarp();
         tmem_ld_32x32(lane_addr + c * 32, sv);
@@ -492,7 +500,8 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tc_fence_after();
     }
 #pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = half * 4 + cc;  // half 0 stores dV (TMEM columns 256..383), half 1 stores dK (384..511)
       uint32_t o[32];
       __syncwarp();
       if (n > 0) {
@@ -579,9 +588,9 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
     attr_set = true;
   }
   dim3 grid((T + ATT_BM - 1) / ATT_BM, H, B);
-  attn_tc_dq_kernel<<<grid, 192, AttnDqSmem::BYTES, stream>>>(tm_qkv, tm_dy, p, C);
+  attn_tc_dq_kernel<<<grid, ATT_THREADS_BWD, AttnDqSmem::BYTES, stream>>>(tm_qkv, tm_dy, p, C);
   rc = check_launch("attn_tc_dq");
   if (rc) return rc;
-  attn_tc_dkv_kernel<<<grid, 192, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_dy, p, C);
+  attn_tc_dkv_kernel<<<grid, ATT_THREADS_BWD, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_dy, p, C);
   return check_launch("attn_tc_dkv");
 }

@@ -72,7 +72,10 @@ __device__ __forceinline__ void keep4(const AttnTcParams& p, unsigned long long 
   ks[3] = ((rnd.w >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? s : 0.f;
 }
 
-// named barrier among the 128 compute threads (warps 2..5)
-__device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// named barrier among the 256 compute threads (warps 2..9)
+__device__ __forceinline__ void compute_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+constexpr int ATT_COMPUTE_WARPS = 8;
+constexpr int ATT_THREADS_BWD = 64 + 32 * ATT_COMPUTE_WARPS;
 
 }  // namespace obt

@@ -340,7 +340,7 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   p.num_m = static_cast<int>((M + bm - 1) / bm);
   p.num_n = static_cast<int>((N + GEMM_BN - 1) / GEMM_BN);
   p.num_kb = static_cast<int>((K + GEMM_BK - 1) / GEMM_BK);
-  p.epi = epilogue;
+  p.epi = (epilogue == EPI_GELU && gelu_mode == 1) ? EPI_GELU_EAGER : epilogue;
   p.gelu_mode = gelu_mode;
   p.D = static_cast<__nv_bfloat16*>(D);
   p.ldd = ldd;

@@ -1,11 +1,15 @@
 // GEMM epilogue: TMEM -> registers -> (swizzled smem transpose) -> coalesced, fused global stores.
 //
 // tcgen05.ld hands each thread one accumulator ROW, so storing straight from those registers makes every warp-wide
-// store touch 32 different 128-byte lines (the first ncu capture showed L1TEX at 83 % and the tensor pipe at 41 %).
-// Instead each epilogue warp stages its 32 rows x 64 columns (bf16, 128 B per row) in a 4 KB XOR-swizzled smem
-// buffer and reads it back with 8 lanes per row, so every global access of the fused epilogue (residual / U loads,
-// D / U stores) is a full 128-byte line per 8 lanes. All epilogues start from rb(acc), which is exactly what the
-// staged bf16 value is.
+// store touch 32 different 128-byte lines (first ncu capture: L1TEX 83 %, tensor pipe 41 %, profiles/r01_gemm_v0_*).
+// Instead each epilogue warp stages 32 rows x 64 columns (bf16, 128 B per row) in a 4 KB XOR-swizzled smem buffer
+// and reads it back with 8 lanes per row, so every global access of the fused epilogue (residual / U loads, D / U
+// stores) is a full 128-byte line per 8 lanes. All epilogues start from rb(acc), which is exactly the staged bf16.
+//
+// The epilogue kind is a template parameter of the inner loops (one switch per tile, none per element) and the aux
+// loads of a 64-column chunk are issued back to back before any math: the second capture
+// (profiles/r01_gemm_v2_gelu_epilogue.details.txt) showed the runtime-switched version issue-bound at ~56
+// instructions per element and the residual variant latency-bound on dependent load->store pairs.
 #pragma once
 #include "ptx.cuh"
 
@@ -18,6 +22,7 @@ enum : int {
   EPI_GELU_BWD = 3,  // D = rb(float(rb(acc)) * gelu'(float(aux_in)))      (aux_in = U saved by EPI_GELU)
   EPI_PARTIAL = 4,   // split-K: fp32 partial tile -> workspace[split]
   EPI_RESID_DROPOUT = 5,  // D = rb(float(aux_in) + float(rb(rb(acc) * keep/(1-p))))   (resid_dropout, model.py:151,167)
+  EPI_GELU_EAGER = 6,     // internal: EPI_GELU with one bf16 rounding per primitive (gelu_mode = 1)
 };
 
 struct GemmParams {
@@ -43,13 +48,13 @@ constexpr uint32_t GEMM_STAGE_BYTES_PER_WARP = 32 * 128;  // epilogue staging: 3
 constexpr int GEMM_EPI_WARPS = 8;                          // two per TMEM lane quadrant
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;     // warp 0 = TMA, warp 1 = MMA, warps 2.. = epilogue
 
-// 1 + erf(t) and exp(-t^2) in ~14 instructions (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7, no cancellation on the
-// negative side). libdevice erff costs ~40 instructions and made the GELU epilogues 5-8x longer than the main loop
-// (profiles/r01_launches_v1.txt); the result is rounded to bf16 (2^-9 relative) right after.
+// 1 + erf(t) and exp(-t^2) in ~15 instructions (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7, no cancellation on the
+// negative side); the result is rounded to bf16 (2^-9 relative) right after. libdevice erff costs ~40.
 __device__ __forceinline__ void one_plus_erf(float t, float& cdf2, float& e) {
   const float a = fabsf(t);
-  const float k = __frcp_rn(fmaf(0.3275911f, a, 1.0f));
-  e = __expf(-a * a);
+  float k;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(k) : "f"(fmaf(0.3275911f, a, 1.0f)));  // 1 MUFU, rel. error 2^-23
+  e = fast_ex2(a * a * -1.4426950408889634f);
   float poly = fmaf(1.061405429f, k, -1.453152027f);
   poly = fmaf(poly, k, 1.421413741f);
   poly = fmaf(poly, k, -0.284496736f);
@@ -58,14 +63,15 @@ __device__ __forceinline__ void one_plus_erf(float t, float& cdf2, float& e) {
   cdf2 = (t >= 0.f) ? 2.0f - pe : pe;   // = 1 + erf(t)
 }
 
-__device__ __forceinline__ float gelu_ref(float x, int mode) {
-  // reference: x * 0.5 * (1.0 + erf(x / 1.41421))  -- the constant is 1.41421, not sqrt(2) (model.py:25)
-  if (mode == 0) {
-    float cdf2, e;
-    one_plus_erf(x * (1.0f / 1.41421f), cdf2, e);
-    return x * 0.5f * cdf2;
-  }
-  // per-primitive bf16 rounding (un-fused TorchScript / CPU eager execution of the same expression)
+// reference: x * 0.5 * (1.0 + erf(x / 1.41421))  -- the constant is 1.41421, not sqrt(2) (model.py:25)
+__device__ __forceinline__ float gelu_fused(float x) {
+  float cdf2, e;
+  one_plus_erf(x * (1.0f / 1.41421f), cdf2, e);
+  return (0.5f * x) * cdf2;
+}
+
+// same expression with one bf16 rounding per primitive (un-fused TorchScript / CPU eager execution)
+__device__ __noinline__ float gelu_eager(float x) {
   float a = rb(x * 0.5f);
   float b = rb(x / 1.41421f);
   float c = rb(erff(b));
@@ -78,7 +84,7 @@ __device__ __forceinline__ float gelu_grad_ref(float x) {
   float cdf2, e;
   one_plus_erf(x * inv, cdf2, e);
   // d/dx [x * 0.5 * (1 + erf(x/c))] = 0.5 (1 + erf(x/c)) + x * 0.5 * 2/sqrt(pi) * exp(-(x/c)^2) / c
-  return 0.5f * cdf2 + x * (0.5f * 1.1283791670955126f * inv) * e;
+  return fmaf(x * (0.5f * 1.1283791670955126f * inv), e, 0.5f * cdf2);
 }
 
 __device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
@@ -89,59 +95,50 @@ __device__ __forceinline__ uint4 pack8f(const float (&f)[8]) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
 
-__device__ __forceinline__ void load8(const __nv_bfloat16* src, bool vec, int nvalid, float (&f)[8]) {
-  if (vec) {
-    unpack8f(*reinterpret_cast<const uint4*>(src), f);
-  } else {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = (e < nvalid) ? __bfloat162float(src[e]) : 0.f;
-  }
-}
-__device__ __forceinline__ void store8(__nv_bfloat16* dst, bool vec, int nvalid, const float (&f)[8]) {
-  if (vec) {
-    *reinterpret_cast<uint4*>(dst) = pack8f(f);
-  } else {
-#pragma unroll
-    for (int e = 0; e < 8; ++e)
-      if (e < nvalid) dst[e] = __float2bfloat16_rn(f[e]);
-  }
-}
+template <int EPI>
+struct EpiTraits {
+  static constexpr bool kAuxIn = (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_RESID_DROPOUT);
+  static constexpr bool kAuxOut = (EPI == EPI_GELU || EPI == EPI_GELU_EAGER);
+};
 
-// One 8-element (16-byte) segment of an output row: v holds rb(acc) for columns [gcol, gcol+8) of row grow.
-__device__ __forceinline__ void epilogue_segment(const GemmParams& p, float (&v)[8], long long grow, int gcol) {
-  const int nvalid = p.N - gcol;  // > 0 by construction
-  const bool vec = p.vec_ok && nvalid >= 8;
-  if (p.epi == EPI_RESID || p.epi == EPI_GELU_BWD || p.epi == EPI_RESID_DROPOUT) {
-    float a[8];
-    load8(p.aux_in + grow * p.ld_aux_in + gcol, vec, nvalid, a);
-    if (p.epi == EPI_RESID) {
+// v: rb(acc) for 8 consecutive columns; a: aux_in values (when the epilogue has one). Returns D in v, U in u.
+template <int EPI>
+__device__ __forceinline__ void epilogue_math(const GemmParams& p, float (&v)[8], const float (&a)[8], float (&u)[8],
+                                              long long grow, int gcol) {
+  if constexpr (EPI == EPI_RESID) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = a[e] + v[e];
-    } else if (p.epi == EPI_GELU_BWD) {
+    for (int e = 0; e < 8; ++e) v[e] = a[e] + v[e];
+  } else if constexpr (EPI == EPI_GELU_BWD) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = v[e] * gelu_grad_ref(a[e]);
-    } else {
-      // resid dropout: one Philox call per 4 consecutive columns, keyed by the flat element index row*N + col
-      const float scale = 1.0f / (1.0f - p.drop_p);
-      const unsigned long long base = (static_cast<unsigned long long>(grow) * p.N + gcol) >> 2;
+    for (int e = 0; e < 8; ++e) v[e] = v[e] * gelu_grad_ref(a[e]);
+  } else if constexpr (EPI == EPI_RESID_DROPOUT) {
+    // one RNG call per 4 consecutive columns, keyed by the flat element index row*N + col
+    const float scale = 1.0f / (1.0f - p.drop_p);
+    const unsigned long long base = (static_cast<unsigned long long>(grow) * p.N + gcol) >> 2;
 #pragma unroll
-      for (int j4 = 0; j4 < 2; ++j4) {
-        const uint4 rnd = rand4x32(p.seed, base + j4, p.offset);
-        const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+    for (int j4 = 0; j4 < 2; ++j4) {
+      const uint4 rnd = rand4x32(p.seed, base + j4, p.offset);
+      const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float u01 = (rr[e] >> 8) * (1.0f / 16777216.0f);
-          const float d = (u01 >= p.drop_p) ? rb(v[4 * j4 + e] * scale) : 0.f;
-          v[4 * j4 + e] = a[4 * j4 + e] + d;
-        }
+      for (int e = 0; e < 4; ++e) {
+        const float u01 = (rr[e] >> 8) * (1.0f / 16777216.0f);
+        const float d = (u01 >= p.drop_p) ? rb(v[4 * j4 + e] * scale) : 0.f;
+        v[4 * j4 + e] = a[4 * j4 + e] + d;
       }
     }
-  } else if (p.epi == EPI_GELU) {
-    store8(p.aux_out + grow * p.ld_aux_out + gcol, vec, nvalid, v);
+  } else if constexpr (EPI == EPI_GELU) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = gelu_ref(v[e], p.gelu_mode);
+    for (int e = 0; e < 8; ++e) {
+      u[e] = v[e];
+      v[e] = gelu_fused(v[e]);
+    }
+  } else if constexpr (EPI == EPI_GELU_EAGER) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      u[e] = v[e];
+      v[e] = gelu_eager(v[e]);
+    }
   }
-  store8(p.D + grow * p.ldd + gcol, vec, nvalid, v);
 }
 
 // Stage one thread-row of 8 x 16-byte chunks (chunk k of row `lane` goes to slot k ^ (lane & 7)).
@@ -195,10 +192,32 @@ __device__ __forceinline__ void partial_readback(const GemmParams& p, const uint
   }
 }
 
-// Whole 128 x 256 accumulator slice of one epilogue warp: rows row_base..row_base+31 (TMEM lanes of this warp's
-// quadrant), columns n0..n0+255.
-__device__ __forceinline__ void epilogue_warp_tile(const GemmParams& p, uint32_t taddr, uint8_t* stage, int lane,
-                                                   long long row_base, int n0, int split, int c_begin, int c_end) {
+// Rare path: ragged N / unaligned pointers. Element-wise with bounds checks, runtime-dispatched, kept out of line.
+template <int EPI>
+__device__ __noinline__ void epilogue_segment_slow(const GemmParams& p, uint4 w, long long grow, int gcol) {
+  float v[8], a[8], u[8];
+  unpack8f(w, v);
+  const int nvalid = p.N - gcol;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    a[e] = 0.f;
+    if constexpr (EpiTraits<EPI>::kAuxIn)
+      if (e < nvalid) a[e] = __bfloat162float(p.aux_in[grow * p.ld_aux_in + gcol + e]);
+  }
+  epilogue_math<EPI>(p, v, a, u, grow, gcol);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (e < nvalid) {
+      if constexpr (EpiTraits<EPI>::kAuxOut) p.aux_out[grow * p.ld_aux_out + gcol + e] = __float2bfloat16_rn(u[e]);
+      p.D[grow * p.ldd + gcol + e] = __float2bfloat16_rn(v[e]);
+    }
+  }
+}
+
+// 64-column chunks [c_begin, c_end) of this warp's 32 accumulator rows.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t taddr, uint8_t* stage, int lane,
+                                                long long row_base, int n0, int split, int c_begin, int c_end) {
   const int rsub = lane >> 3, seg = lane & 7;
 #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
@@ -209,7 +228,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const GemmParams& p, uint32_t
     tmem_ld_32x32(taddr + c * 64, r0);
     tmem_ld_32x32(taddr + c * 64 + 32, r1);
     tmem_ld_wait();
-    if (p.epi == EPI_PARTIAL) {
+    if constexpr (EPI == EPI_PARTIAL) {
       stage_write_f32(stage, lane, r0);
       __syncwarp();
       partial_readback(p, stage, lane, row_base, col_base, split);
@@ -218,23 +237,66 @@ __device__ __forceinline__ void epilogue_warp_tile(const GemmParams& p, uint32_t
       __syncwarp();
       partial_readback(p, stage, lane, row_base, col_base + 32, split);
       __syncwarp();
-      continue;
-    }
-    stage_write_bf16(stage, lane, r0, r1);
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rl = it * 4 + rsub;
-      const long long grow = row_base + rl;
+    } else {
+      stage_write_bf16(stage, lane, r0, r1);
+      __syncwarp();
       const int gcol = col_base + seg * 8;
-      const uint4 w = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((seg ^ (rl & 7)) << 4));
-      if (grow < p.M && gcol < p.N) {
-        float v[8];
-        unpack8f(w, v);
-        epilogue_segment(p, v, grow, gcol);
+      const bool col_ok = gcol < p.N;
+      const bool vec = p.vec_ok && (p.N - gcol >= 8);
+      // two groups of 4 row-iterations (keeps the unrolled code of each epilogue variant within the I-cache)
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {
+        uint4 w[4], ax[4];
+        // staged values and aux loads of the group first (independent loads in flight together) ...
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rl = (hf * 4 + it) * 4 + rsub;
+          w[it] = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((seg ^ (rl & 7)) << 4));
+          if constexpr (EpiTraits<EPI>::kAuxIn) {
+            const long long grow = row_base + rl;
+            ax[it] = make_uint4(0, 0, 0, 0);
+            if (vec && grow < p.M) ax[it] = *reinterpret_cast<const uint4*>(p.aux_in + grow * p.ld_aux_in + gcol);
+          }
+        }
+        // ... then the math and the stores
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rl = (hf * 4 + it) * 4 + rsub;
+          const long long grow = row_base + rl;
+          if (grow < p.M && col_ok) {
+            if (vec) {
+              float v[8], a[8], u[8];
+              unpack8f(w[it], v);
+              if constexpr (EpiTraits<EPI>::kAuxIn) unpack8f(ax[it], a);
+              epilogue_math<EPI>(p, v, a, u, grow, gcol);
+              if constexpr (EpiTraits<EPI>::kAuxOut)
+                *reinterpret_cast<uint4*>(p.aux_out + grow * p.ld_aux_out + gcol) = pack8f(u);
+              *reinterpret_cast<uint4*>(p.D + grow * p.ldd + gcol) = pack8f(v);
+            } else {
+              epilogue_segment_slow<EPI>(p, w[it], grow, gcol);
+            }
+          }
+        }
       }
+      __syncwarp();  // the staging buffer is reused by the next 64-column chunk
     }
-    __syncwarp();  // the staging buffer is reused by the next 64-column chunk
+  }
+}
+
+// Whole accumulator slice of one epilogue warp: rows row_base..row_base+31 (TMEM lanes of this warp's quadrant),
+// 64-column chunks [c_begin, c_end) of the tile starting at column n0. One switch per tile.
+__device__ __forceinline__ void epilogue_warp_tile(const GemmParams& p, uint32_t taddr, uint8_t* stage, int lane,
+                                                   long long row_base, int n0, int split, int c_begin, int c_end) {
+  switch (p.epi) {
+    case EPI_PLAIN: epilogue_chunks<EPI_PLAIN>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
+    case EPI_RESID: epilogue_chunks<EPI_RESID>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
+    case EPI_GELU: epilogue_chunks<EPI_GELU>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
+    case EPI_GELU_BWD: epilogue_chunks<EPI_GELU_BWD>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
+    case EPI_PARTIAL: epilogue_chunks<EPI_PARTIAL>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
+    case EPI_RESID_DROPOUT:
+      epilogue_chunks<EPI_RESID_DROPOUT>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end);
+      break;
+    default: epilogue_chunks<EPI_GELU_EAGER>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
   }
 }
 
