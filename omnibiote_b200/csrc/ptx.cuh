@@ -315,12 +315,16 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t subseq, uint
 // (Philox4x32-10 above costs ~100 dependent integer ops per call; with one softmax warp per scheduler that latency
 // dominated the attention kernels. The reference's dropout stream is torch's own, so parity is statistical anyway.)
 __device__ __forceinline__ uint4 rand4x32(uint64_t seed, uint64_t ctr, uint64_t offset) {
-  uint64_t z = ctr * 0x9E3779B97F4A7C15ull + (seed ^ (offset * 0xD1B54A32D192ED03ull));
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  const uint32_t lo = static_cast<uint32_t>(z), hi = static_cast<uint32_t>(z >> 32);
-  return make_uint4(lo << 16, lo & 0xFFFF0000u, hi << 16, hi & 0xFFFF0000u);
+  // stream key (loop-invariant at every call site, hoisted by the compiler)
+  const uint64_t key = seed ^ (offset * 0xD1B54A32D192ED03ull);
+  const uint32_t k0 = static_cast<uint32_t>(key), k1 = static_cast<uint32_t>(key >> 32);
+  const uint32_t c0 = static_cast<uint32_t>(ctr), c1 = static_cast<uint32_t>(ctr >> 32);
+  // two 32-bit murmur3 finalisers over differently keyed counters (32-bit integer ops only)
+  uint32_t a = (c0 * 0x9E3779B1u) ^ k0 ^ (c1 * 0x85EBCA77u);
+  uint32_t b = (c0 * 0xC2B2AE3Du) + k1 + (c1 * 0x27D4EB2Fu);
+  a ^= a >> 16; a *= 0x85EBCA6Bu; a ^= a >> 13; a *= 0xC2B2AE35u; a ^= a >> 16;
+  b ^= b >> 16; b *= 0x7FEB352Du; b ^= b >> 15; b *= 0x846CA68Bu; b ^= b >> 16;
+  return make_uint4(a << 16, a & 0xFFFF0000u, b << 16, b & 0xFFFF0000u);
 }
 
 }  // namespace obt

@@ -206,45 +206,66 @@ __global__ void ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bf
 // LayerNorm backward (dy is first divided by dy_div and rounded: the MuReadout 1/width_mult adjoint). dx = rb( (dres ? dres : 0) + rb(rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat))) )
 // dgamma partial sums (fp32) are written per block into dgamma_partial[gridDim.x][C].
 template <int kMaxChunks>
-__global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(256, kMaxChunks == 4 ? 2 : 1)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                               const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean_in,
                               const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ dres,
                               __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma_partial, long long M, int C,
                               float dy_div) {
-  extern __shared__ float s_dg[];  // [warps][C]
+  // dgamma partial sums live in shared memory, laid out [warp][chunk i][j][lane] (lane fastest: conflict-free), so
+  // the row loop needs ~70 registers and three 256-thread blocks fit per SM (the register-resident version ran one
+  // block per SM and reached 1.6 TB/s; see profiles/r01_launches_v3.txt).
+  extern __shared__ float s_dg[];
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nchunks = C / 8;
-  float dg[kMaxChunks][8];
+  float* my_dg = s_dg + static_cast<size_t>(warp) * kMaxChunks * 256;
 #pragma unroll
   for (int i = 0; i < kMaxChunks; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dg[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) my_dg[(i * 8 + j) * 32 + lane] = 0.f;
 
   for (long long row = static_cast<long long>(blockIdx.x) * warps_per_block + warp; row < M;
        row += static_cast<long long>(gridDim.x) * warps_per_block) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
     const uint4* dsrc = reinterpret_cast<const uint4*>(dy + row * C);
     const uint4* xsrc = reinterpret_cast<const uint4*>(x + row * C);
-    float a[kMaxChunks][8], xh[kMaxChunks][8];
+    const uint4* rsrc = dres ? reinterpret_cast<const uint4*>(dres + row * C) : nullptr;
+    uint4 pd[kMaxChunks], px[kMaxChunks], pr[kMaxChunks];
+    // all loads of the row first
+#pragma unroll
+    for (int i = 0; i < kMaxChunks; ++i) {
+      const int c = lane + 32 * i;
+      pd[i] = px[i] = pr[i] = make_uint4(0, 0, 0, 0);
+      if (c < nchunks) {
+        pd[i] = dsrc[c];
+        px[i] = xsrc[c];
+        if (rsrc) pr[i] = rsrc[c];
+      }
+    }
+    const float mean = mean_in[row], rstd = rstd_in[row];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < kMaxChunks; ++i) {
       const int c = lane + 32 * i;
       if (c < nchunks) {
         float d[8], g[8], xv[8];
-        unpack8(dsrc[c], d);
-        unpack8(xsrc[c], xv);
+        unpack8(pd[i], d);
+        unpack8(px[i], xv);
         unpack8(reinterpret_cast<const uint4*>(gamma)[c], g);
+        if (dy_div != 1.0f) {
+          // MuReadout adjoint: the reference divides by width_mult and rounds to bf16 before ln_f's backward
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = rb(d[j] / dy_div);
+          pd[i] = pack8(d);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float dyv = (dy_div != 1.0f) ? rb(d[j] / dy_div) : d[j];
-          xh[i][j] = (xv[j] - mean) * rstd;
-          a[i][j] = dyv * g[j];
-          dg[i][j] += dyv * xh[i][j];
-          s1 += a[i][j];
-          s2 += a[i][j] * xh[i][j];
+          const float xh = (xv[j] - mean) * rstd;
+          const float a = d[j] * g[j];
+          my_dg[(i * 8 + j) * 32 + lane] += d[j] * xh;
+          s1 += a;
+          s2 += a * xh;
         }
       }
     }
@@ -255,33 +276,30 @@ __global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_b
     for (int i = 0; i < kMaxChunks; ++i) {
       const int c = lane + 32 * i;
       if (c < nchunks) {
-        float o[8];
+        float d[8], g[8], xv[8], r[8], o[8];
+        unpack8(pd[i], d);
+        unpack8(px[i], xv);
+        unpack8(pr[i], r);
+        unpack8(reinterpret_cast<const uint4*>(gamma)[c], g);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rb(rstd * (a[i][j] - s1 - xh[i][j] * s2));
-        if (dres) {
-          float r[8];
-          unpack8(reinterpret_cast<const uint4*>(dres + row * C)[c], r);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mean) * rstd;
+          o[j] = rb(rstd * (d[j] * g[j] - s1 - xh * s2)) + r[j];
         }
         dst[c] = pack8(o);
       }
     }
   }
-  // block reduction of dgamma partials
-#pragma unroll
-  for (int i = 0; i < kMaxChunks; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nchunks) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s_dg[warp * C + c * 8 + j] = dg[i][j];
-    }
-  }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float t = 0.f;
-    for (int w = 0; w < warps_per_block; ++w) t += s_dg[w * C + c];
-    dgamma_partial[static_cast<long long>(blockIdx.x) * C + c] = t;
+  // block reduction of the per-warp dgamma partials; column of (i, j, lane) = (lane + 32 i) * 8 + j
+  for (int t = threadIdx.x; t < kMaxChunks * 256; t += blockDim.x) {
+    const int ln = t & 31, ij = t >> 5;
+    const int col = (ln + 32 * (ij >> 3)) * 8 + (ij & 7);
+    if (col < C) {
+      float acc = 0.f;
+      for (int w = 0; w < warps_per_block; ++w) acc += s_dg[static_cast<size_t>(w) * kMaxChunks * 256 + t];
+      dgamma_partial[static_cast<long long>(blockIdx.x) * C + col] = acc;
+    }
   }
 }
 
@@ -528,7 +546,7 @@ extern "C" int obt_layernorm_bwd(const void* dy, const void* x, const void* gamm
   int grid = sm_count() * 4;
   if (M < static_cast<long long>(grid) * wpb) grid = static_cast<int>((M + wpb - 1) / wpb);
   if (grid < 1) grid = 1;
-  const size_t smem = static_cast<size_t>(wpb) * C * sizeof(float);
+  const size_t smem = static_cast<size_t>(wpb) * ((C <= 1024) ? 4 : 8) * 256 * sizeof(float);
   auto a = static_cast<const __nv_bfloat16*>(dy);
   auto b = static_cast<const __nv_bfloat16*>(x);
   auto g = static_cast<const __nv_bfloat16*>(gamma);
