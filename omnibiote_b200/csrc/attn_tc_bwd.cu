@@ -1,12 +1,18 @@
 // Attention backward on tcgen05 tensor cores (head_dim = 128): the adjoint of attn_tc.cu.
 //
 //   delta_i = dO_i . O_i                                   (attn_delta_kernel, memory-bound pre-pass)
-//   dQ kernel : one CTA per 128-query tile, loops over KV tiles:  S = Q K^T, dP = dO V^T (TMEM),
+//   dQ kernel : one CTA per 128-query tile, loops over 64-key sub-tiles:  S = Q K^T, dP = dO V^T (TMEM),
 //               dS = P o (dP - delta) * scale -> bf16 smem tile,   dQ += dS K   (accumulated in TMEM)
-//   dKV kernel: one CTA per 128-key tile, loops over query tiles: S^T = K Q^T, dP^T = V dO^T (TMEM),
+//   dKV kernel: one CTA per 128-key tile, loops over 64-query sub-tiles: S^T = K Q^T, dP^T = V dO^T (TMEM),
 //               P^T, dS^T -> bf16 smem tiles,   dV += P^T dO,   dK += dS^T Q   (accumulated in TMEM)
 // P is recomputed from the forward's (row max, log exp-sum) pair. Splitting dQ from dK/dV recomputes S and dP once
 // more (7 instead of 5 tile products) but needs no atomics and keeps every accumulator in TMEM.
+//
+// Pipelining (v3): the score tiles are 64 wide so that S/dP fit TWICE in TMEM next to the gradient accumulators
+// (2 x 128 + 128 columns for dQ, 2 x 128 + 256 for dV/dK = all 512). The MMA thread issues the score products of
+// sub-tile s+1 before the gradient products of sub-tile s, so the 8 compute warps (two threads per TMEM lane, 32
+// columns each) always have a finished score tile to work on while the tensor pipe is busy (v2 alternated between
+// the two and measured 552 / 789 us per layer, profiles/r01_launches_v3.txt).
 // The Q / dO / K / V smem tiles written by TMA serve both as K-major operands (scores) and, read through an
 // MN-major descriptor, as the [reduction x 128] operands of the gradient products: no transposes are materialised.
 #include "attn_tc_common.cuh"
@@ -34,15 +40,46 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dy, long lon
   }
 }
 
+// D[128 x 64] = A[128 x 128(d)] * B[64 x 128(d)]^T, both K-major; a tile = two 64-column sub-tiles `a_sub` /
+// `b_sub` bytes apart.
+__device__ __forceinline__ void issue_scores_128x64(uint32_t d_tmem, uint32_t a_addr, uint32_t a_sub, uint32_t b_addr,
+                                                    uint32_t b_sub) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, false);
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const uint64_t a_desc = make_smem_desc_sw128(a_addr + (kk >> 2) * a_sub + (kk & 3) * 32, 0, 1024);
+    const uint64_t b_desc = make_smem_desc_sw128(b_addr + (kk >> 2) * b_sub + (kk & 3) * 32, 0, 1024);
+    umma_bf16_ss<1>(d_tmem, a_desc, b_desc, idesc, kk > 0 ? 1u : 0u);
+  }
+}
+
+// D[128 x 128(d)] += A[128 x 64] * B[64 x 128(d)]: A is a K-major [128 x 64] tile (one 128-byte row per lane),
+// B is read MN-major from a TMA-written [64 rows x 128] tile whose two 64-column halves are `b_lbo` bytes apart.
+__device__ __forceinline__ void issue_grad_128x128x64(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t b_lbo,
+                                                      bool accumulate) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, true);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const uint64_t a_desc = make_smem_desc_sw128(a_addr + kk * 32, 0, 1024);
+    const uint64_t b_desc = make_smem_desc_sw128(b_addr + kk * 2048, b_lbo, 1024);
+    umma_bf16_ss<1>(d_tmem, a_desc, b_desc, idesc, (accumulate || kk > 0) ? 1u : 0u);
+  }
+}
+
+// byte offset of the 16-byte chunk [c, c+8) of row r in a [128 x 64] bf16 K-major tile (128-byte rows, 128B swizzle)
+__device__ __forceinline__ uint32_t sw128_row64_off(int r, int c) {
+  return static_cast<uint32_t>(r * 128 + (((c >> 3) ^ (r & 7)) << 4));
+}
+
 // =============================================================================================
 // dQ kernel
 // =============================================================================================
 struct AttnDqSmem {
   static constexpr uint32_t Q_OFF = 0;
   static constexpr uint32_t DO_OFF = Q_OFF + ATT_TILE_BYTES;
-  static constexpr uint32_t K_OFF = DO_OFF + ATT_TILE_BYTES;      // 2 stages
+  static constexpr uint32_t K_OFF = DO_OFF + ATT_TILE_BYTES;      // 2 stages of 128 keys
   static constexpr uint32_t V_OFF = K_OFF + 2 * ATT_TILE_BYTES;   // 2 stages
-  static constexpr uint32_t DS_OFF = V_OFF + 2 * ATT_TILE_BYTES;
+  static constexpr uint32_t DS_OFF = V_OFF + 2 * ATT_TILE_BYTES;  // 2 buffers of [128 x 64] (16 KB each)
   static constexpr uint32_t BAR_OFF = DS_OFF + ATT_TILE_BYTES;
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
@@ -59,15 +96,14 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
   uint8_t* sDS = smem + AttnDqSmem::DS_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnDqSmem::BAR_OFF);
   uint64_t* qdo_full = bars + 0;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* k_empty = bars + 3;   // [2]
-  uint64_t* v_full = bars + 5;    // [2]
-  uint64_t* v_empty = bars + 7;   // [2]
-  uint64_t* sdp_full = bars + 9;
-  uint64_t* ds_full = bars + 10;
-  uint64_t* dq_done = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  int* s_range = reinterpret_cast<int*>(bars + 13);
+  uint64_t* k_full = bars + 1;     // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;     // [2]
+  uint64_t* sdp_full = bars + 7;   // [2]
+  uint64_t* ds_full = bars + 9;    // [2]
+  uint64_t* buf_free = bars + 11;  // [2]  dQ MMA of the sub-tile that used score/dS buffer b has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  int* s_range = reinterpret_cast<int*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.x * ATT_BM;
@@ -80,13 +116,12 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
     mbar_init(qdo_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&sdp_full[i], 1);
+      mbar_init(&ds_full[i], ATT_COMPUTE_WARPS);
+      mbar_init(&buf_free[i], 1);
     }
-    mbar_init(sdp_full, 1);
-    mbar_init(ds_full, ATT_COMPUTE_WARPS);
-    mbar_init(dq_done, 1);
     fence_barrier_init();
     s_range[0] = T;
     s_range[1] = 0;
@@ -113,7 +148,8 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
     jb = s_range[0] / ATT_BN;
     je = (s_range[1] + ATT_BN - 1) / ATT_BN;
   }
-  const int n_tiles = je - jb;
+  const int n_tiles = je - jb;   // 128-key tiles
+  const int n_sub = 2 * n_tiles;  // 64-key sub-tiles
   const int row0 = b * T;
   const int qcol = h * ATT_D, kcol = C + h * ATT_D, vcol = 2 * C + h * ATT_D;
 
@@ -128,11 +164,10 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
         const int st = jj & 1;
         const uint32_t par = (jj >> 1) & 1;
         const int krow = row0 + (jb + jj) * ATT_BN;
-        mbar_wait(&k_empty[st], par ^ 1);
+        mbar_wait(&kv_empty[st], par ^ 1);
         mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
         tma_load_2d(&tm_qkv, &k_full[st], sK + st * ATT_TILE_BYTES, kcol, krow);
         tma_load_2d(&tm_qkv, &k_full[st], sK + st * ATT_TILE_BYTES + 16384, kcol + 64, krow);
-        mbar_wait(&v_empty[st], par ^ 1);
         mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
         tma_load_2d(&tm_qkv, &v_full[st], sV + st * ATT_TILE_BYTES, vcol, krow);
         tma_load_2d(&tm_qkv, &v_full[st], sV + st * ATT_TILE_BYTES + 16384, vcol + 64, krow);
@@ -142,27 +177,36 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
     if (lane == 0) {
       const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), ds_addr = smem_u32(sDS);
       mbar_wait(qdo_full, 0);
-      for (int jj = 0; jj < n_tiles; ++jj) {
-        const int st = jj & 1;
-        const uint32_t par = (jj >> 1) & 1;
-        const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES), v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
-        mbar_wait(&k_full[st], par);
-        mbar_wait(&v_full[st], par);
+      // scores of sub-tile s: S -> buffer (s&1) columns [0,64), dP -> columns [64,128)
+      auto issue_scores = [&](int s) {
+        const int jj = s >> 1, hsub = s & 1, st = jj & 1;
+        if (hsub == 0) {
+          mbar_wait(&k_full[st], (jj >> 1) & 1);
+          mbar_wait(&v_full[st], (jj >> 1) & 1);
+        }
         tc_fence_after();
-        issue_128x128x128<false>(tmem_base, q_addr, k_addr, false);         // S  = Q K^T
-        issue_128x128x128<false>(tmem_base + 128, do_addr, v_addr, false);  // dP = dO V^T
-        umma_commit(sdp_full);
-        mbar_wait(ds_full, jj & 1);
+        const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES) + hsub * 8192;
+        const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES) + hsub * 8192;
+        const uint32_t d = tmem_base + (s & 1) * 128;
+        issue_scores_128x64(d, q_addr, 16384, k_addr, 16384);
+        issue_scores_128x64(d + 64, do_addr, 16384, v_addr, 16384);
+        umma_commit(&sdp_full[s & 1]);
+      };
+      issue_scores(0);
+      for (int s = 0; s < n_sub; ++s) {
+        if (s + 1 < n_sub) issue_scores(s + 1);  // buffer (s+1)&1 was drained before dQ(s-1) was issued
+        const int jj = s >> 1, hsub = s & 1, st = jj & 1;
+        mbar_wait(&ds_full[s & 1], (s >> 1) & 1);
         tc_fence_after();
-        issue_128x128x128<true>(tmem_base + 256, ds_addr, k_addr, jj > 0);  // dQ += dS K
-        umma_commit(dq_done);
-        umma_commit(&k_empty[st]);
-        umma_commit(&v_empty[st]);
+        const uint32_t k_rows = smem_u32(sK + st * ATT_TILE_BYTES) + hsub * 8192;  // key rows 64*hsub .. of the tile
+        issue_grad_128x128x64(tmem_base + 256, ds_addr + (s & 1) * 16384, k_rows, 16384, s > 0);  // dQ += dS K
+        umma_commit(&buf_free[s & 1]);
+        if (hsub == 1) umma_commit(&kv_empty[st]);
       }
     }
   } else {
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;  // two threads per query row: key columns / dQ columns [64*half, 64*half+64)
+    const int hh = (warp - 2) >> 2;  // two threads per query row: columns [32*hh, +32) of every 64-key sub-tile
     const int r = q * 32 + lane;
     const int i = t0 + r;
     const bool row_ok = i < T;
@@ -175,71 +219,71 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
       if (lo >= hi) { lo = 0; hi = T; row_scale = 0.f; }
     }
     const long long bh = static_cast<long long>(b) * p.H + h;
-    float off = 0.f, ls2 = 0.f, dl = 0.f;
+    float off_nat = 0.f, ls2 = 0.f, dl = 0.f;  // row max (natural units), log-sum in log2 units, delta
     if (row_ok) {
-      off = p.lse[2 * (bh * T + i)];
+      off_nat = p.lse[2 * (bh * T + i)];
       ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
       dl = p.delta[bh * T + i];
     }
+    const float neg = off_nat * LOG2E + ls2;  // interval / no-mask path: the max is a plain score, safe to fold
+    const float sc2 = row_scale * LOG2E;
     const __nv_bfloat16* mrow =
         (p.mask != nullptr && row_ok) ? p.mask + b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq : nullptr;
     const bool use_drop = p.drop_p > 0.f;
 
-    for (int jj = 0; jj < n_tiles; ++jj) {
-      const int j0 = (jb + jj) * ATT_BN;
-      mbar_wait(sdp_full, jj & 1);
+    for (int s = 0; s < n_sub; ++s) {
+      const int bsel = s & 1;
+      const int j0 = (jb + (s >> 1)) * ATT_BN + (s & 1) * 64 + hh * 32;  // first key of this thread's 32 columns
+      mbar_wait(&sdp_full[bsel], (s >> 1) & 1);
       tc_fence_after();
-      if (jj > 0) mbar_wait(dq_done, (jj - 1) & 1);  // previous dS tile fully consumed
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
-        uint32_t sv[32], dv[32];
-        __syncwarp();
-        tmem_ld_32x32(lane_addr + c * 32, sv);
-        tmem_ld_32x32(lane_addr + 128 + c * 32, dv);
-        tmem_ld_wait();
-        float ds[32];
+      if (s >= 2) mbar_wait(&buf_free[bsel], ((s >> 1) - 1) & 1);  // dS buffer consumed by dQ of sub-tile s-2
+      uint32_t sv[32], dv[32];
+      __syncwarp();
+      tmem_ld_32x32(lane_addr + bsel * 128 + hh * 32, sv);
+      tmem_ld_32x32(lane_addr + bsel * 128 + 64 + hh * 32, dv);
+      tmem_ld_wait();
+      float ds[32];
 #pragma unroll
-        for (int g4 = 0; g4 < 8; ++g4) {
-          float ks[4] = {1.f, 1.f, 1.f, 1.f};
-          if (use_drop && row_ok)
-            keep4(p, ((static_cast<unsigned long long>(bh) * T + i) * T) + static_cast<unsigned long long>(j0 + c * 32 + g4 * 4), ks);
+      for (int g4 = 0; g4 < 8; ++g4) {
+        float ks[4] = {1.f, 1.f, 1.f, 1.f};
+        if (use_drop && row_ok)
+          keep4(p, ((static_cast<unsigned long long>(bh) * T + i) * T) + static_cast<unsigned long long>(j0 + g4 * 4), ks);
 #pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            const int e = g4 * 4 + e4;
-            const int j = j0 + c * 32 + e;
-            float sp;
-            bool vis;
-            if (mrow != nullptr) {
-              vis = j < T;
-              const float bias = vis ? __bfloat162float(mrow[j]) : 0.f;
-              sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
-            } else {
-              vis = (j >= lo && j < hi);
-              sp = __uint_as_float(sv[e]) * row_scale;
-            }
-            const float pr = (vis && row_ok) ? fast_exp2((sp - off) * LOG2E - ls2) : 0.f;
-            ds[e] = pr * (__uint_as_float(dv[e]) * ks[e4] - dl) * row_scale;
+        for (int e4 = 0; e4 < 4; ++e4) {
+          const int e = g4 * 4 + e4;
+          const int j = j0 + e;
+          float pr;
+          if (mrow != nullptr) {
+            const bool vis = j < T;
+            const float bias = vis ? __bfloat162float(mrow[j]) : 0.f;
+            const float sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
+            pr = vis ? fast_exp2((sp - off_nat) * LOG2E - ls2) : 0.f;
+          } else {
+            pr = (j >= lo && j < hi && row_ok) ? fast_exp2(__uint_as_float(sv[e]) * sc2 - neg) : 0.f;
           }
+          ds[e] = pr * (__uint_as_float(dv[e]) * ks[e4] - dl) * row_scale;
         }
+      }
+      uint8_t* dsb = sDS + bsel * 16384;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint4 w = make_uint4(pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]), pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]),
-                                     pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]), pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]));
-          *reinterpret_cast<uint4*>(sDS + sw128_chunk_off(r, c * 32 + g * 8)) = w;
-        }
+      for (int g = 0; g < 4; ++g) {
+        const uint4 w = make_uint4(pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]), pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]),
+                                   pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]), pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]));
+        *reinterpret_cast<uint4*>(dsb + sw128_row64_off(r, hh * 32 + g * 8)) = w;
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full);
+      if (lane == 0) mbar_arrive(&ds_full[bsel]);
     }
-    mbar_wait(dq_done, (n_tiles - 1) & 1);
+    // dQ epilogue: this thread stores columns [64*hh, 64*hh+64) of its row
+    const int last = n_sub - 1;
+    mbar_wait(&buf_free[last & 1], (last >> 1) & 1);
     tc_fence_after();
     __nv_bfloat16* drow = p.dq + (static_cast<long long>(row0) + i) * p.ldd + h * ATT_D;
 #pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
-      const int c = half * 2 + cc;
+      const int c = hh * 2 + cc;
       uint32_t o[32];
       __syncwarp();
       tmem_ld_32x32(lane_addr + 256 + c * 32, o);
@@ -266,23 +310,25 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
 // =============================================================================================
 // dK / dV kernel
 // =============================================================================================
+constexpr uint32_t ATT_SUB_BYTES = 64 * 128 * 2;  // one [64 rows x 128] bf16 tile = two 8 KB swizzle sub-tiles
+
 struct AttnDkvSmem {
   static constexpr uint32_t K_OFF = 0;
   static constexpr uint32_t V_OFF = K_OFF + ATT_TILE_BYTES;
-  static constexpr uint32_t Q_OFF = V_OFF + ATT_TILE_BYTES;
-  static constexpr uint32_t DO_OFF = Q_OFF + ATT_TILE_BYTES;
-  static constexpr uint32_t PT_OFF = DO_OFF + ATT_TILE_BYTES;
-  static constexpr uint32_t DST_OFF = PT_OFF + ATT_TILE_BYTES;
-  // per-query (column) parameters: float4 {lo, hi, scale*log2e, max*log2e + logsum*log2e}, float2 {delta, scale},
-  // and the 128-key dropout keep bitmask of each query row (4 words)
-  static constexpr uint32_t COL_OFF = DST_OFF + ATT_TILE_BYTES;
-  static constexpr uint32_t BAR_OFF = COL_OFF + 128 * 16 + 128 * 8 + 128 * 16;
+  static constexpr uint32_t Q_OFF = V_OFF + ATT_TILE_BYTES;          // 2 stages of 64 queries (16 KB each)
+  static constexpr uint32_t DO_OFF = Q_OFF + 2 * ATT_SUB_BYTES;      // 2 stages
+  static constexpr uint32_t PT_OFF = DO_OFF + 2 * ATT_SUB_BYTES;     // 2 buffers [128 keys x 64 q] (16 KB each)
+  static constexpr uint32_t DST_OFF = PT_OFF + 2 * 16384;            // 2 buffers
+  // per-query (column) parameters, double buffered: float4 {lo, hi, scale*log2e, (max+logsum)*log2e},
+  // float4 {delta, scale, max (natural), logsum*log2e}, uint4 keep bits of the 128 keys
+  static constexpr uint32_t COL_OFF = DST_OFF + 2 * 16384;
+  static constexpr uint32_t BAR_OFF = COL_OFF + 2 * 64 * 48;
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
 
 __global__ void __launch_bounds__(ATT_THREADS_BWD, 1)
-attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dy,
-                   const AttnTcParams p, int C) {
+attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_q64,
+                   const __grid_constant__ CUtensorMap tm_dy64, const AttnTcParams p, int C) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem + AttnDkvSmem::K_OFF;
@@ -291,54 +337,57 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint8_t* sDO = smem + AttnDkvSmem::DO_OFF;
   uint8_t* sPT = smem + AttnDkvSmem::PT_OFF;
   uint8_t* sDST = smem + AttnDkvSmem::DST_OFF;
-  float4* c_a = reinterpret_cast<float4*>(smem + AttnDkvSmem::COL_OFF);
-  float2* c_b = reinterpret_cast<float2*>(c_a + 128);
-  uint4* c_keep = reinterpret_cast<uint4*>(c_b + 128);
+  uint8_t* sCol = smem + AttnDkvSmem::COL_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnDkvSmem::BAR_OFF);
   uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;
-  uint64_t* qdo_empty = bars + 2;
-  uint64_t* sdp_full = bars + 3;
-  uint64_t* pds_full = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-  unsigned int* s_rel = reinterpret_cast<unsigned int*>(bars + 6);  // relevance bitmask of query tiles (<= 64 tiles)
+  uint64_t* qdo_full = bars + 1;  // [2]
+  uint64_t* done = bars + 3;      // [2] dV/dK MMAs of the sub-tile using stage/buffer b completed (frees Q/dO/P^T/dS^T)
+  uint64_t* sdp_full = bars + 5;  // [2]
+  uint64_t* pds_full = bars + 7;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  unsigned int* s_rel = reinterpret_cast<unsigned int*>(bars + 10);  // relevance bits of the 64-query sub-tiles (<=128)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j0 = blockIdx.x * ATT_BN;
   const int h = blockIdx.y, b = blockIdx.z;
   const int T = p.T;
-  const int nq = (T + ATT_BM - 1) / ATT_BM;
+  const int nq = (T + 63) / 64;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
-    tma_prefetch_desc(&tm_dy);
+    tma_prefetch_desc(&tm_q64);
+    tma_prefetch_desc(&tm_dy64);
     mbar_init(kv_full, 1);
-    mbar_init(qdo_full, 1);
-    mbar_init(qdo_empty, 1);
-    mbar_init(sdp_full, 1);
-    mbar_init(pds_full, ATT_COMPUTE_WARPS);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&done[i], 1);
+      mbar_init(&sdp_full[i], 1);
+      mbar_init(&pds_full[i], ATT_COMPUTE_WARPS);
+    }
     fence_barrier_init();
-    s_rel[0] = 0;
-    s_rel[1] = 0;
+    s_rel[0] = s_rel[1] = s_rel[2] = s_rel[3] = 0;
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
   __syncthreads();
-  // which query tiles can see this key tile at all
+  // which 64-query sub-tiles can see this key tile at all
   if (p.row_lo != nullptr) {
     for (int i = threadIdx.x; i < T; i += blockDim.x) {
       const int lo = p.row_lo[static_cast<long long>(b) * T + i], hi = p.row_hi[static_cast<long long>(b) * T + i];
       const bool rel = (lo >= hi) || (lo < j0 + ATT_BN && hi > j0);
-      if (rel) atomicOr(&s_rel[(i / ATT_BM) >> 5], 1u << ((i / ATT_BM) & 31));
+      if (rel) atomicOr(&s_rel[(i >> 6) >> 5], 1u << ((i >> 6) & 31));
     }
-  } else if (threadIdx.x == 0) {
-    s_rel[0] = 0xffffffffu;
-    s_rel[1] = 0xffffffffu;
+  } else if (threadIdx.x < 4) {
+    s_rel[threadIdx.x] = 0xffffffffu;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-  const unsigned long long rel = (static_cast<unsigned long long>(s_rel[1]) << 32) | s_rel[0];
+  const unsigned int rel0 = s_rel[0], rel1 = s_rel[1], rel2 = s_rel[2], rel3 = s_rel[3];
+  auto relevant = [&](int it) -> bool {
+    const unsigned int w = (it >> 5) == 0 ? rel0 : (it >> 5) == 1 ? rel1 : (it >> 5) == 2 ? rel2 : rel3;
+    return (w >> (it & 31)) & 1u;
+  };
   const int row0 = b * T;
   const int qcol = h * ATT_D, kcol = C + h * ATT_D, vcol = 2 * C + h * ATT_D;
 
@@ -351,157 +400,166 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tma_load_2d(&tm_qkv, kv_full, sV + 16384, vcol + 64, row0 + j0);
       int n = 0;
       for (int it = 0; it < nq; ++it) {
-        if (!((rel >> it) & 1ull)) continue;
-        mbar_wait(qdo_empty, (n & 1) ^ 1);
-        mbar_expect_tx(qdo_full, 2 * ATT_TILE_BYTES);
-        const int qrow = row0 + it * ATT_BM;
-        tma_load_2d(&tm_qkv, qdo_full, sQ, qcol, qrow);
-        tma_load_2d(&tm_qkv, qdo_full, sQ + 16384, qcol + 64, qrow);
-        tma_load_2d(&tm_dy, qdo_full, sDO, qcol, qrow);
-        tma_load_2d(&tm_dy, qdo_full, sDO + 16384, qcol + 64, qrow);
+        if (!relevant(it)) continue;
+        const int st = n & 1;
+        mbar_wait(&done[st], ((n >> 1) & 1) ^ 1);
+        mbar_expect_tx(&qdo_full[st], 2 * ATT_SUB_BYTES);
+        const int qrow = row0 + it * 64;
+        tma_load_2d(&tm_q64, &qdo_full[st], sQ + st * ATT_SUB_BYTES, qcol, qrow);
+        tma_load_2d(&tm_q64, &qdo_full[st], sQ + st * ATT_SUB_BYTES + 8192, qcol + 64, qrow);
+        tma_load_2d(&tm_dy64, &qdo_full[st], sDO + st * ATT_SUB_BYTES, qcol, qrow);
+        tma_load_2d(&tm_dy64, &qdo_full[st], sDO + st * ATT_SUB_BYTES + 8192, qcol + 64, qrow);
         ++n;
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
-      const uint32_t pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      int n_total = 0;
+      for (int it = 0; it < nq; ++it) n_total += relevant(it) ? 1 : 0;
       mbar_wait(kv_full, 0);
-      int n = 0;
-      for (int it = 0; it < nq; ++it) {
-        if (!((rel >> it) & 1ull)) continue;
-        mbar_wait(qdo_full, n & 1);
+      auto issue_scores = [&](int n) {
+        const int st = n & 1;
+        mbar_wait(&qdo_full[st], (n >> 1) & 1);
         tc_fence_after();
-        issue_128x128x128<false>(tmem_base, k_addr, q_addr, false);         // S^T  = K Q^T
-        issue_128x128x128<false>(tmem_base + 128, v_addr, do_addr, false);  // dP^T = V dO^T
-        umma_commit(sdp_full);
-        mbar_wait(pds_full, n & 1);
+        const uint32_t d = tmem_base + st * 128;
+        issue_scores_128x64(d, k_addr, 16384, smem_u32(sQ + st * ATT_SUB_BYTES), 8192);        // S^T  = K Q^T
+        issue_scores_128x64(d + 64, v_addr, 16384, smem_u32(sDO + st * ATT_SUB_BYTES), 8192);  // dP^T = V dO^T
+        umma_commit(&sdp_full[st]);
+      };
+      if (n_total > 0) issue_scores(0);
+      for (int n = 0; n < n_total; ++n) {
+        if (n + 1 < n_total) issue_scores(n + 1);
+        const int st = n & 1;
+        mbar_wait(&pds_full[st], (n >> 1) & 1);
         tc_fence_after();
-        issue_128x128x128<true>(tmem_base + 256, pt_addr, do_addr, n > 0);  // dV += P^T dO
-        issue_128x128x128<true>(tmem_base + 384, dst_addr, q_addr, n > 0);  // dK += dS^T Q
-        umma_commit(qdo_empty);
-        ++n;
+        issue_grad_128x128x64(tmem_base + 256, smem_u32(sPT + st * 16384), smem_u32(sDO + st * ATT_SUB_BYTES), 8192,
+                              n > 0);  // dV += P^T dO
+        issue_grad_128x128x64(tmem_base + 384, smem_u32(sDST + st * 16384), smem_u32(sQ + st * ATT_SUB_BYTES), 8192,
+                              n > 0);  // dK += dS^T Q
+        umma_commit(&done[st]);
       }
     }
   } else {
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;  // two threads per key row: query columns [64*half, +64); dV (0) / dK (1) epilogue
-    const int r = q * 32 + lane;  // key row within the tile
+    const int hh = (warp - 2) >> 2;  // two threads per key row: query columns [32*hh, +32) of every 64-query sub-tile
+    const int r = q * 32 + lane;     // key row within the tile
     const int j = j0 + r;
     const bool key_ok = j < T;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const long long bh = static_cast<long long>(b) * p.H + h;
     const bool use_drop = p.drop_p > 0.f;
+    const float keep_scale = use_drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    const int ct = threadIdx.x - 64;  // 0..255 among the compute threads
     int n = 0;
     for (int it = 0; it < nq; ++it) {
-      if (!((rel >> it) & 1ull)) continue;
-      const int i0 = it * ATT_BM;
-      // per-query parameters of this tile (thread r loads query i0 + r) + dropout keep bits of its 128 keys
-      compute_bar_sync256();
+      if (!relevant(it)) continue;
+      const int st = n & 1;
+      const int i0 = it * 64;
+      float4* c_a = reinterpret_cast<float4*>(sCol + st * (64 * 48));
+      float4* c_b = c_a + 64;
+      uint32_t* c_keep = reinterpret_cast<uint32_t*>(c_b + 64);  // [64 queries][4 words]
+      // parameters of the 64 queries (threads 0..63) and dropout keep bits (all 256 threads: query ct&63, keys
+      // [32*(ct>>6), +32)); the buffer was last read two sub-tiles ago, separated by the barrier of the previous one
       {
-        const int i = i0 + r;
-        int lo = 0, hi = 0;  // query beyond the sequence: contributes nothing
-        float sc = p.scale, off = 0.f, ls2 = 0.f, dl = 0.f;
-        if (i < T) {
-          lo = 0; hi = T;
-          if (p.row_lo != nullptr) {
-            lo = p.row_lo[static_cast<long long>(b) * T + i];
-            hi = p.row_hi[static_cast<long long>(b) * T + i];
-            if (lo >= hi) { lo = 0; hi = T; sc = 0.f; }
+        const int qi = ct & 63, quarter = ct >> 6;
+        const int i = i0 + qi;
+        if (ct < 64) {
+          int lo = 0, hi = 0;  // query beyond the sequence: contributes nothing
+          float sc = p.scale, off = 0.f, ls2 = 0.f, dl = 0.f;
+          if (i < T) {
+            lo = 0; hi = T;
+            if (p.row_lo != nullptr) {
+              lo = p.row_lo[static_cast<long long>(b) * T + i];
+              hi = p.row_hi[static_cast<long long>(b) * T + i];
+              if (lo >= hi) { lo = 0; hi = T; sc = 0.f; }
+            }
+            off = p.lse[2 * (bh * T + i)];
+            ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
+            dl = p.delta[bh * T + i];
           }
-          off = p.lse[2 * (bh * T + i)];
-          ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
-          dl = p.delta[bh * T + i];
-        }
-        if (half == 0) {
-          c_a[r] = make_float4(__int_as_float(lo), __int_as_float(hi), sc * LOG2E, off * LOG2E + ls2);
-          c_b[r] = make_float2(dl, sc);
+          c_a[qi] = make_float4(__int_as_float(lo), __int_as_float(hi), sc * LOG2E, off * LOG2E + ls2);
+          c_b[qi] = make_float4(dl, sc, off, ls2);
         }
         if (use_drop) {
-          // this thread generates the keep bits of keys [64*half, 64*half+64) of query row i0 + r
-          uint32_t bits[2] = {0u, 0u};
+          uint32_t bits = 0u;
           if (i < T) {
-            const unsigned long long e0 = (static_cast<unsigned long long>(bh) * T + i) * T + static_cast<unsigned long long>(j0);
-#pragma unroll 4
-            for (int g = 0; g < 16; ++g) {
-              const uint4 rnd = rand4x32(p.seed, (e0 >> 2) + half * 16 + g, p.offset);
+            const unsigned long long e0 =
+                (static_cast<unsigned long long>(bh) * T + i) * T + static_cast<unsigned long long>(j0 + quarter * 32);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const uint4 rnd = rand4x32(p.seed, (e0 >> 2) + g, p.offset);
               uint32_t nib = 0;
               nib |= ((rnd.x >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 1u : 0u;
               nib |= ((rnd.y >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 2u : 0u;
               nib |= ((rnd.z >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 4u : 0u;
               nib |= ((rnd.w >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 8u : 0u;
-              bits[g >> 3] |= nib << ((g & 7) * 4);
+              bits |= nib << (g * 4);
             }
           }
-          reinterpret_cast<uint2*>(c_keep + r)[half] = make_uint2(bits[0], bits[1]);
+          c_keep[qi * 4 + quarter] = bits;
         }
       }
       compute_bar_sync256();
-      mbar_wait(sdp_full, n & 1);
+      mbar_wait(&sdp_full[st], (n >> 1) & 1);
       tc_fence_after();
-      if (n > 0) mbar_wait(qdo_empty, (n - 1) & 1);  // previous P^T / dS^T tiles fully consumed
-      const float keep_scale = use_drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
-        uint32_t sv[32], dv[32];
-        __syncwarp();
-        tmem_ld_32x32(lane_addr + c * 32, sv);
-        tmem_ld_32x32(lane_addr + 128 + c * 32, dv);
-        tmem_ld_wait();
-        float pt[32], dst[32];
+      if (n >= 2) mbar_wait(&done[st], ((n >> 1) - 1) & 1);  // P^T / dS^T buffers consumed by sub-tile n-2
+      uint32_t sv[32], dv[32];
+      __syncwarp();
+      tmem_ld_32x32(lane_addr + st * 128 + hh * 32, sv);
+      tmem_ld_32x32(lane_addr + st * 128 + 64 + hh * 32, dv);
+      tmem_ld_wait();
+      float pt[32], dst[32];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int col = c * 32 + e;
-          const int i = i0 + col;
-          const float4 ca = c_a[col];
-          const float2 cb = c_b[col];
-          float pr;
-          if (p.mask != nullptr) {
-            const bool vis = key_ok && i < T;
-            const float bias = vis ? __bfloat162float(p.mask[b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq + j]) : 0.f;
-            const float sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
-            pr = vis ? fast_exp2(sp * LOG2E - ca.w) : 0.f;
-          } else {
-            const bool vis = key_ok && j >= __float_as_int(ca.x) && j < __float_as_int(ca.y);
-            pr = vis ? fast_exp2(__uint_as_float(sv[e]) * ca.z - ca.w) : 0.f;
-          }
-          float ks = 1.0f;
-          if (use_drop) {
-            const uint4 kb = c_keep[col];
-            const uint32_t word = q == 0 ? kb.x : q == 1 ? kb.y : q == 2 ? kb.z : kb.w;
-            ks = ((word >> lane) & 1u) ? keep_scale : 0.f;
-          }
-          pt[e] = pr * ks;
-          dst[e] = pr * (__uint_as_float(dv[e]) * ks - cb.x) * cb.y;
+      for (int e = 0; e < 32; ++e) {
+        const int col = hh * 32 + e;
+        const int i = i0 + col;
+        const float4 ca = c_a[col];
+        const float4 cb = c_b[col];
+        float pr;
+        if (p.mask != nullptr) {
+          const bool vis = key_ok && i < T;
+          const float bias = vis ? __bfloat162float(p.mask[b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq + j]) : 0.f;
+          const float sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
+          pr = vis ? fast_exp2((sp - cb.z) * LOG2E - cb.w) : 0.f;
+        } else {
+          const bool vis = key_ok && j >= __float_as_int(ca.x) && j < __float_as_int(ca.y);
+          pr = vis ? fast_exp2(__uint_as_float(sv[e]) * ca.z - ca.w) : 0.f;
         }
+        float ks = 1.0f;
+        if (use_drop) ks = ((c_keep[col * 4 + q] >> lane) & 1u) ? keep_scale : 0.f;
+        pt[e] = pr * ks;
+        dst[e] = pr * (__uint_as_float(dv[e]) * ks - cb.x) * cb.y;
+      }
+      uint8_t* ptb = sPT + st * 16384;
+      uint8_t* dsb = sDST + st * 16384;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t o = sw128_chunk_off(r, c * 32 + g * 8);
-          *reinterpret_cast<uint4*>(sPT + o) =
-              make_uint4(pack_bf16x2(pt[g * 8 + 0], pt[g * 8 + 1]), pack_bf16x2(pt[g * 8 + 2], pt[g * 8 + 3]),
-                         pack_bf16x2(pt[g * 8 + 4], pt[g * 8 + 5]), pack_bf16x2(pt[g * 8 + 6], pt[g * 8 + 7]));
-          *reinterpret_cast<uint4*>(sDST + o) =
-              make_uint4(pack_bf16x2(dst[g * 8 + 0], dst[g * 8 + 1]), pack_bf16x2(dst[g * 8 + 2], dst[g * 8 + 3]),
-                         pack_bf16x2(dst[g * 8 + 4], dst[g * 8 + 5]), pack_bf16x2(dst[g * 8 + 6], dst[g * 8 + 7]));
-        }
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t o = sw128_row64_off(r, hh * 32 + g * 8);
+        *reinterpret_cast<uint4*>(ptb + o) =
+            make_uint4(pack_bf16x2(pt[g * 8 + 0], pt[g * 8 + 1]), pack_bf16x2(pt[g * 8 + 2], pt[g * 8 + 3]),
+                       pack_bf16x2(pt[g * 8 + 4], pt[g * 8 + 5]), pack_bf16x2(pt[g * 8 + 6], pt[g * 8 + 7]));
+        *reinterpret_cast<uint4*>(dsb + o) =
+            make_uint4(pack_bf16x2(dst[g * 8 + 0], dst[g * 8 + 1]), pack_bf16x2(dst[g * 8 + 2], dst[g * 8 + 3]),
+                       pack_bf16x2(dst[g * 8 + 4], dst[g * 8 + 5]), pack_bf16x2(dst[g * 8 + 6], dst[g * 8 + 7]));
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
+      if (lane == 0) mbar_arrive(&pds_full[st]);
       ++n;
     }
-    // epilogue: dV, dK rows of this key
+    // epilogue: hh = 0 stores dV (TMEM columns 256..383), hh = 1 stores dK (384..511) of this key row
     __nv_bfloat16* dvrow = p.dv + (static_cast<long long>(row0) + j) * p.ldd + h * ATT_D;
     __nv_bfloat16* dkrow = p.dk + (static_cast<long long>(row0) + j) * p.ldd + h * ATT_D;
     if (n > 0) {
-      mbar_wait(qdo_empty, (n - 1) & 1);
+      const int last = n - 1;
+      mbar_wait(&done[last & 1], (last >> 1) & 1);
       tc_fence_after();
     }
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
-      const int c = half * 4 + cc;  // half 0 stores dV (TMEM columns 256..383), half 1 stores dK (384..511)
+      const int c = hh * 4 + cc;
       uint32_t o[32];
       __syncwarp();
       if (n > 0) {
@@ -512,10 +570,10 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         for (int e = 0; e < 32; ++e) o[e] = 0u;
       }
       if (key_ok) {
-        __nv_bfloat16* dst = (c < 4 ? dvrow : dkrow) + (c & 3) * 32;
+        __nv_bfloat16* dstp = (c < 4 ? dvrow : dkrow) + (c & 3) * 32;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          reinterpret_cast<uint4*>(dst)[g] = make_uint4(
+          reinterpret_cast<uint4*>(dstp)[g] = make_uint4(
               pack_bf16x2(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1])),
               pack_bf16x2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3])),
               pack_bf16x2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5])),
@@ -543,18 +601,24 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
   OBT_REQUIRE(qkv && y && dy && lse && delta && dqkv, "obt_attn_tc_bwd: null pointer");
   OBT_REQUIRE(d == ATT_D, "obt_attn_tc_bwd: head_dim=%d, the tensor-core kernel is specialised for 128", d);
   OBT_REQUIRE(B > 0 && H > 0 && T > 0, "obt_attn_tc_bwd: empty problem");
-  OBT_REQUIRE(T <= 64 * ATT_BM, "obt_attn_tc_bwd: T=%d exceeds %d", T, 64 * ATT_BM);
+  OBT_REQUIRE(T <= 128 * 64, "obt_attn_tc_bwd: T=%d exceeds %d", T, 128 * 64);
   OBT_REQUIRE(ld % 8 == 0 && ldy % 8 == 0 && lddy % 8 == 0 && ldd % 8 == 0, "obt_attn_tc_bwd: pitches must be multiples of 8");
   OBT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "obt_attn_tc_bwd: dropout p=%f", drop_p);
   OBT_REQUIRE(drop_p == 0.f || T % 4 == 0, "obt_attn_tc_bwd: attention dropout needs T %% 4 == 0 (T=%d)", T);
   const int C = H * d;
   const long long M = static_cast<long long>(B) * T;
-  CUtensorMap tm_qkv, tm_dy;
+  CUtensorMap tm_qkv, tm_dy, tm_q64, tm_dy64;
   int rc = get_tensor_map_2d(&tm_qkv, qkv, static_cast<uint64_t>(3) * C, static_cast<uint64_t>(M),
                              static_cast<uint64_t>(ld), 64, 128);
   if (rc) return rc;
   rc = get_tensor_map_2d(&tm_dy, dy, static_cast<uint64_t>(C), static_cast<uint64_t>(M), static_cast<uint64_t>(lddy), 64,
                          128);
+  if (rc) return rc;
+  rc = get_tensor_map_2d(&tm_q64, qkv, static_cast<uint64_t>(3) * C, static_cast<uint64_t>(M), static_cast<uint64_t>(ld),
+                         64, 64);
+  if (rc) return rc;
+  rc = get_tensor_map_2d(&tm_dy64, dy, static_cast<uint64_t>(C), static_cast<uint64_t>(M), static_cast<uint64_t>(lddy), 64,
+                         64);
   if (rc) return rc;
   {
     const int warps = 8;
@@ -591,6 +655,6 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
   attn_tc_dq_kernel<<<grid, ATT_THREADS_BWD, AttnDqSmem::BYTES, stream>>>(tm_qkv, tm_dy, p, C);
   rc = check_launch("attn_tc_dq");
   if (rc) return rc;
-  attn_tc_dkv_kernel<<<grid, ATT_THREADS_BWD, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_dy, p, C);
+  attn_tc_dkv_kernel<<<grid, ATT_THREADS_BWD, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
   return check_launch("attn_tc_dkv");
 }

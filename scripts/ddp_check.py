@@ -32,7 +32,9 @@ def main():
     model = make_model(2, 256, H, vocab, T, seed=rank).train()     # different seeds ...
     for p in model.parameters():
         dist.broadcast(p.data, 0)                                   # ... made identical like DDP's constructor
-    ref_model = copy.deepcopy(model)
+    # (copy.deepcopy drops Parameter.__dict__, hence mup's infshape — same as in the reference)
+    ref_model = make_model(2, 256, H, vocab, T, seed=rank).train()
+    ref_model.load_state_dict(model.state_dict())
     g = torch.Generator().manual_seed(123)
     ids_all = torch.randint(20, vocab, (world, mbs, T), generator=g)
     ids_all[:, :, T // 2] = 3
