@@ -178,6 +178,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     const __nv_bfloat16* mrow =
         (p.mask != nullptr && row_ok) ? p.mask + b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq : nullptr;
     const bool use_drop = p.drop_p > 0.f;
+    // keep <=> u01 >= p with u01 = (w >> 8) * 2^-24  <=>  (w >> 8) >= ceil(p * 2^24): same decision as every other
+    // dropout site of the library, as one integer compare
+    const uint32_t drop_thr = static_cast<uint32_t>(ceilf(p.drop_p * 16777216.0f));
+    const float drop_scale = 1.0f / (1.0f - p.drop_p);
     float m_run = -INFINITY, l_run = 0.f;  // running max (log2 domain, whole row) and exp-sum (this half only)
 
     for (int jj = 0; jj < n_tiles; ++jj) {
@@ -195,13 +199,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         __syncwarp();
         tmem_ld_32x32(s_addr + c * 32, v);
         tmem_ld_wait();
-        if (mrow != nullptr) {
-          const uint4* mp = reinterpret_cast<const uint4*>(mrow + j0 + c * 32);
+        if (p.mask != nullptr) {  // warp-uniform (rows beyond T have mrow == nullptr and read no bias)
+          const uint4* mp = reinterpret_cast<const uint4*>((mrow ? mrow : p.mask) + j0 + c * 32);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int jbase = j0 + c * 32 + g * 8;
             uint4 mu = make_uint4(0, 0, 0, 0);
-            if (jbase + 8 <= T) mu = mp[g];
+            if (jbase + 8 <= T && mrow != nullptr) mu = mp[g];
             const uint32_t mw[4] = {mu.x, mu.y, mu.z, mu.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -211,6 +215,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
               tmax = fmaxf(tmax, s);
             }
           }
+        } else if (__all_sync(0xffffffffu, (j0 + c * 32 >= lo) && (j0 + c * 32 + 32 <= hi))) {
+          // every key of this chunk is visible to every row of the warp (interior of a document): no per-element
+          // interval tests; the (non-negative) scale is applied once to the maximum
+          float mx = __uint_as_float(v[0]);
+#pragma unroll
+          for (int e = 1; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+          tmax = fmaxf(tmax, mx * row_scale);
         } else {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
@@ -257,13 +268,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         tmem_ld_32x32(s_addr + c * 32, v);
         tmem_ld_wait();
         float pr[32];
-        if (mrow != nullptr) {
-          const uint4* mp = reinterpret_cast<const uint4*>(mrow + j0 + c * 32);
+        if (p.mask != nullptr) {  // warp-uniform (rows beyond T have mrow == nullptr and read no bias)
+          const uint4* mp = reinterpret_cast<const uint4*>((mrow ? mrow : p.mask) + j0 + c * 32);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int jbase = j0 + c * 32 + g * 8;
             uint4 mu = make_uint4(0, 0, 0, 0);
-            if (jbase + 8 <= T) mu = mp[g];
+            if (jbase + 8 <= T && mrow != nullptr) mu = mp[g];
             const uint32_t mw[4] = {mu.x, mu.y, mu.z, mu.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -272,6 +283,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
               pr[g * 8 + e] = (jbase + e < T) ? fast_exp2(s - m_use) : 0.f;
             }
           }
+        } else if (__all_sync(0xffffffffu, (j0 + c * 32 >= lo) && (j0 + c * 32 + 32 <= hi))) {
+          const float nm = -m_use;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) pr[e] = fast_exp2(fmaf(__uint_as_float(v[e]), row_scale, nm));
         } else {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
@@ -288,10 +303,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
               ((static_cast<unsigned long long>(b) * p.H + h) * T + i) * T + static_cast<unsigned long long>(j0 + c * 32);
 #pragma unroll
           for (int g4 = 0; g4 < 8; ++g4) {
-            float ks[4];
-            keep4(p, e0 + 4 * g4, ks);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) pr[g4 * 4 + e] *= ks[e];
+            const uint4 rnd = rand4x32(p.seed, (e0 >> 2) + g4, p.offset);
+            pr[g4 * 4 + 0] = ((rnd.x >> 8) >= drop_thr) ? pr[g4 * 4 + 0] * drop_scale : 0.f;
+            pr[g4 * 4 + 1] = ((rnd.y >> 8) >= drop_thr) ? pr[g4 * 4 + 1] * drop_scale : 0.f;
+            pr[g4 * 4 + 2] = ((rnd.z >> 8) >= drop_thr) ? pr[g4 * 4 + 2] * drop_scale : 0.f;
+            pr[g4 * 4 + 3] = ((rnd.w >> 8) >= drop_thr) ? pr[g4 * 4 + 3] * drop_scale : 0.f;
           }
         }
 #pragma unroll

@@ -230,6 +230,8 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
     const __nv_bfloat16* mrow =
         (p.mask != nullptr && row_ok) ? p.mask + b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq : nullptr;
     const bool use_drop = p.drop_p > 0.f;
+    const uint32_t drop_thr = static_cast<uint32_t>(ceilf(p.drop_p * 16777216.0f));  // == (u01 >= p) on 24-bit u01
+    const float drop_scale = 1.0f / (1.0f - p.drop_p);
 
     for (int s = 0; s < n_sub; ++s) {
       const int bsel = s & 1;
@@ -242,27 +244,44 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
       tmem_ld_32x32(lane_addr + bsel * 128 + hh * 32, sv);
       tmem_ld_32x32(lane_addr + bsel * 128 + 64 + hh * 32, dv);
       tmem_ld_wait();
-      float ds[32];
+      float ds[32];  // first P, then dS
+      if (p.mask != nullptr) {  // dense additive bias (warp-uniform branch)
 #pragma unroll
-      for (int g4 = 0; g4 < 8; ++g4) {
-        float ks[4] = {1.f, 1.f, 1.f, 1.f};
-        if (use_drop && row_ok)
-          keep4(p, ((static_cast<unsigned long long>(bh) * T + i) * T) + static_cast<unsigned long long>(j0 + g4 * 4), ks);
-#pragma unroll
-        for (int e4 = 0; e4 < 4; ++e4) {
-          const int e = g4 * 4 + e4;
+        for (int e = 0; e < 32; ++e) {
           const int j = j0 + e;
-          float pr;
-          if (mrow != nullptr) {
-            const bool vis = j < T;
-            const float bias = vis ? __bfloat162float(mrow[j]) : 0.f;
-            const float sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
-            pr = vis ? fast_exp2((sp - off_nat) * LOG2E - ls2) : 0.f;
-          } else {
-            pr = (j >= lo && j < hi && row_ok) ? fast_exp2(__uint_as_float(sv[e]) * sc2 - neg) : 0.f;
-          }
-          ds[e] = pr * (__uint_as_float(dv[e]) * ks[e4] - dl) * row_scale;
+          const bool vis = (j < T) && (mrow != nullptr);
+          const float bias = vis ? __bfloat162float(mrow[j]) : 0.f;
+          const float sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
+          ds[e] = vis ? fast_exp2((sp - off_nat) * LOG2E - ls2) : 0.f;
         }
+      } else if (__all_sync(0xffffffffu, row_ok && j0 >= lo && j0 + 32 <= hi)) {
+        // interior of a document for every row of the warp: no per-element interval tests
+        const float nneg = -neg;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) ds[e] = fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nneg));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int j = j0 + e;
+          ds[e] = (j >= lo && j < hi && row_ok) ? fast_exp2(__uint_as_float(sv[e]) * sc2 - neg) : 0.f;
+        }
+      }
+      if (use_drop) {
+        const unsigned long long e0 =
+            ((static_cast<unsigned long long>(bh) * T + i) * T) + static_cast<unsigned long long>(j0);
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+          const uint4 rnd = rand4x32(p.seed, (e0 >> 2) + g4, p.offset);
+          const float k0 = ((rnd.x >> 8) >= drop_thr) ? drop_scale : 0.f, k1 = ((rnd.y >> 8) >= drop_thr) ? drop_scale : 0.f;
+          const float k2 = ((rnd.z >> 8) >= drop_thr) ? drop_scale : 0.f, k3 = ((rnd.w >> 8) >= drop_thr) ? drop_scale : 0.f;
+          ds[g4 * 4 + 0] *= (__uint_as_float(dv[g4 * 4 + 0]) * k0 - dl) * row_scale;
+          ds[g4 * 4 + 1] *= (__uint_as_float(dv[g4 * 4 + 1]) * k1 - dl) * row_scale;
+          ds[g4 * 4 + 2] *= (__uint_as_float(dv[g4 * 4 + 2]) * k2 - dl) * row_scale;
+          ds[g4 * 4 + 3] *= (__uint_as_float(dv[g4 * 4 + 3]) * k3 - dl) * row_scale;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) ds[e] *= (__uint_as_float(dv[e]) - dl) * row_scale;
       }
       uint8_t* dsb = sDS + bsel * 16384;
 #pragma unroll
@@ -311,6 +330,8 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
 // dK / dV kernel
 // =============================================================================================
 constexpr uint32_t ATT_SUB_BYTES = 64 * 128 * 2;  // one [64 rows x 128] bf16 tile = two 8 KB swizzle sub-tiles
+// 64 x float4 + 64 x int2 + 64 x float2 + 256 keep words + 2 x int2, rounded up
+constexpr uint32_t ATT_COL_STRIDE = 3200;
 
 struct AttnDkvSmem {
   static constexpr uint32_t K_OFF = 0;
@@ -319,10 +340,9 @@ struct AttnDkvSmem {
   static constexpr uint32_t DO_OFF = Q_OFF + 2 * ATT_SUB_BYTES;      // 2 stages
   static constexpr uint32_t PT_OFF = DO_OFF + 2 * ATT_SUB_BYTES;     // 2 buffers [128 keys x 64 q] (16 KB each)
   static constexpr uint32_t DST_OFF = PT_OFF + 2 * 16384;            // 2 buffers
-  // per-query (column) parameters, double buffered: float4 {lo, hi, scale*log2e, (max+logsum)*log2e},
-  // float4 {delta, scale, max (natural), logsum*log2e}, uint4 keep bits of the 128 keys
+  // per-query (column) parameters, double buffered (layout: see ATT_COL_STRIDE users in the kernel)
   static constexpr uint32_t COL_OFF = DST_OFF + 2 * 16384;
-  static constexpr uint32_t BAR_OFF = COL_OFF + 2 * 64 * 48;
+  static constexpr uint32_t BAR_OFF = COL_OFF + 2 * ATT_COL_STRIDE;
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
 
@@ -456,9 +476,11 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       if (!relevant(it)) continue;
       const int st = n & 1;
       const int i0 = it * 64;
-      float4* c_a = reinterpret_cast<float4*>(sCol + st * (64 * 48));
-      float4* c_b = c_a + 64;
-      uint32_t* c_keep = reinterpret_cast<uint32_t*>(c_b + 64);  // [64 queries][4 words]
+      float4* c_p = reinterpret_cast<float4*>(sCol + st * ATT_COL_STRIDE);  // {scale*log2e, (max+lsum)*log2e, delta, scale}
+      int2* c_lh = reinterpret_cast<int2*>(c_p + 64);                       // {lo, hi}
+      float2* c_x = reinterpret_cast<float2*>(c_lh + 64);                   // {max (natural), lsum*log2e} (dense path)
+      uint32_t* c_keep = reinterpret_cast<uint32_t*>(c_x + 64);             // [64 queries][4 words] dropout keep bits
+      int2* c_rng = reinterpret_cast<int2*>(c_keep + 256);                  // per 32-query chunk: {max lo, min hi}
       // parameters of the 64 queries (threads 0..63) and dropout keep bits (all 256 threads: query ct&63, keys
       // [32*(ct>>6), +32)); the buffer was last read two sub-tiles ago, separated by the barrier of the previous one
       {
@@ -478,8 +500,17 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
             dl = p.delta[bh * T + i];
           }
-          c_a[qi] = make_float4(__int_as_float(lo), __int_as_float(hi), sc * LOG2E, off * LOG2E + ls2);
-          c_b[qi] = make_float4(dl, sc, off, ls2);
+          c_p[qi] = make_float4(sc * LOG2E, off * LOG2E + ls2, dl, sc);
+          c_lh[qi] = make_int2(lo, hi);
+          c_x[qi] = make_float2(off, ls2);
+          // threads 0..63 are exactly two warps, one per 32-query chunk: interval common to the whole chunk
+          int mlo = lo, mhi = hi;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            mlo = max(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
+            mhi = min(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
+          }
+          if ((ct & 31) == 0) c_rng[ct >> 5] = make_int2(mlo, mhi);
         }
         if (use_drop) {
           uint32_t bits = 0u;
@@ -510,26 +541,33 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tmem_ld_32x32(lane_addr + st * 128 + 64 + hh * 32, dv);
       tmem_ld_wait();
       float pt[32], dst[32];
+      const int2 rng = c_rng[hh];
+      // every key of this warp visible to every query of the chunk (interior of a document): warp-uniform test
+      const bool interior = (p.mask == nullptr) && (j0 + q * 32 >= rng.x) && (j0 + q * 32 + 32 <= rng.y) &&
+                            (j0 + q * 32 + 32 <= T);
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
         const int col = hh * 32 + e;
-        const int i = i0 + col;
-        const float4 ca = c_a[col];
-        const float4 cb = c_b[col];
+        const float4 cp = c_p[col];
         float pr;
-        if (p.mask != nullptr) {
+        if (interior) {
+          pr = fast_exp2(fmaf(__uint_as_float(sv[e]), cp.x, -cp.y));
+        } else if (p.mask != nullptr) {
+          const int i = i0 + col;
+          const float2 cx = c_x[col];
           const bool vis = key_ok && i < T;
           const float bias = vis ? __bfloat162float(p.mask[b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq + j]) : 0.f;
           const float sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
-          pr = vis ? fast_exp2((sp - cb.z) * LOG2E - cb.w) : 0.f;
+          pr = vis ? fast_exp2((sp - cx.x) * LOG2E - cx.y) : 0.f;
         } else {
-          const bool vis = key_ok && j >= __float_as_int(ca.x) && j < __float_as_int(ca.y);
-          pr = vis ? fast_exp2(__uint_as_float(sv[e]) * ca.z - ca.w) : 0.f;
+          const int2 lh = c_lh[col];
+          const bool vis = key_ok && j >= lh.x && j < lh.y;
+          pr = vis ? fast_exp2(__uint_as_float(sv[e]) * cp.x - cp.y) : 0.f;
         }
         float ks = 1.0f;
         if (use_drop) ks = ((c_keep[col * 4 + q] >> lane) & 1u) ? keep_scale : 0.f;
         pt[e] = pr * ks;
-        dst[e] = pr * (__uint_as_float(dv[e]) * ks - cb.x) * cb.y;
+        dst[e] = pr * (__uint_as_float(dv[e]) * ks - cp.z) * cp.w;
       }
       uint8_t* ptb = sPT + st * 16384;
       uint8_t* dsb = sDST + st * 16384;

@@ -35,20 +35,29 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int num_m, int num_n) 
   return c;
 }
 
-template <int kCG>
+// kMode 1: one CTA per tile (128 x 256), cta_group::1 MMA.
+// kMode 2: CTA pair per 256 x 256 tile, cta_group::2 MMA (each CTA holds half of B, accumulators in both TMEMs).
+// kMode 3: cluster of 2 CTAs on vertically adjacent 128 x 256 tiles sharing the B tile: each CTA TMA-loads half of
+//          B and MULTICASTS it into both CTAs' smem (L2 -> SM operand traffic 48 KB -> 32 KB per k-block per CTA);
+//          the MMAs stay cta_group::1, a smem stage is recycled only when BOTH CTAs' MMAs have consumed it.
+template <int kMode>
 struct GemmCfg {
-  static constexpr int STAGES = kCG == 1 ? 4 : 6;
-  static constexpr int BNL = GEMM_BN / kCG;  // rows of B each CTA loads
+  static constexpr int CG = kMode == 2 ? 2 : 1;        // MMA cta_group
+  static constexpr int CLUSTER = kMode == 1 ? 1 : 2;   // CTAs per cluster = 128-row blocks per tile
+  static constexpr int STAGES = kMode == 2 ? 6 : 4;
+  static constexpr int BNL = GEMM_BN / CG;             // rows of B resident per CTA
   static constexpr uint32_t A_BYTES = GEMM_BM_CTA * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = BNL * GEMM_BK * 2;
   static constexpr uint32_t SMEM_BYTES =
       STAGES * (A_BYTES + B_BYTES) + 256 + GEMM_EPI_WARPS * GEMM_STAGE_BYTES_PER_WARP + 1024;
 };
 
-template <int kCG, bool kAMN, bool kBMN>
+template <int kMode, bool kAMN, bool kBMN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<kCG>;
+  using Cfg = GemmCfg<kMode>;
+  constexpr int kCG = Cfg::CG;
+  constexpr int kCluster = Cfg::CLUSTER;
   constexpr int STAGES = Cfg::STAGES;
   constexpr uint32_t A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES;
 
@@ -66,9 +75,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (kCG == 2) ? cluster_ctarank() : 0u;
-  const int cluster_id = (kCG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
-  const int num_clusters = (kCG == 2) ? (gridDim.x >> 1) : gridDim.x;
+  const uint32_t cta_rank = (kCluster == 2) ? cluster_ctarank() : 0u;
+  const int cluster_id = (kCluster == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const int num_clusters = (kCluster == 2) ? (gridDim.x >> 1) : gridDim.x;
   const int total_tiles = p.num_m * p.num_n * p.splits;
 
   if (warp == 0 && lane == 0) {
@@ -76,7 +85,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], kCG);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], kMode == 3 ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -88,7 +97,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tmem_alloc<kCG>(tmem_slot, 512);
   }
   tc_fence_before();
-  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
+  if constexpr (kCluster == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
@@ -99,8 +108,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const TileCoord tc = tile_coord(tile, p.num_m, p.num_n);
-        const int m0 = tc.m_blk * (GEMM_BM_CTA * kCG) + static_cast<int>(cta_rank) * GEMM_BM_CTA;
-        const int n0 = tc.n_blk * GEMM_BN + static_cast<int>(cta_rank) * Cfg::BNL;
+        const int m0 = tc.m_blk * (GEMM_BM_CTA * kCluster) + static_cast<int>(cta_rank) * GEMM_BM_CTA;
+        const int n0 = tc.n_blk * GEMM_BN + (kMode == 2 ? static_cast<int>(cta_rank) * Cfg::BNL : 0);
         const int kb0 = tc.split * p.kb_per_split;
         const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -108,7 +117,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* a_dst = sA + stage * A_BYTES;
           uint8_t* b_dst = sB + stage * B_BYTES;
           const int k0 = kb * GEMM_BK;
-          if constexpr (kCG == 1) {
+          if constexpr (kMode == 3) {
+            mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
+            if constexpr (!kAMN) {
+              tma_load_2d(&tmA, &full[stage], a_dst, k0, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < GEMM_BM_CTA / 64; ++j) tma_load_2d(&tmA, &full[stage], a_dst + j * 8192, m0 + j * 64, k0);
+            }
+            // this CTA's half of the B tile, multicast into both CTAs (same smem offset, each CTA's own barrier)
+            if constexpr (!kBMN) {
+              tma_load_2d_mc(&tmB, &full[stage], b_dst + cta_rank * 16384, k0, n0 + static_cast<int>(cta_rank) * 128, 0x3);
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                const int j = static_cast<int>(cta_rank) * 2 + jj;
+                tma_load_2d_mc(&tmB, &full[stage], b_dst + j * 8192, n0 + j * 64, k0, 0x3);
+              }
+            }
+          } else if constexpr (kCG == 1) {
             mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
             if constexpr (!kAMN) {
               tma_load_2d(&tmA, &full[stage], a_dst, k0, m0);
@@ -149,7 +176,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && cta_rank == 0) {
+    if (lane == 0 && (kMode != 2 || cta_rank == 0)) {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM_CTA * kCG, GEMM_BN, kAMN, kBMN);
       constexpr uint32_t A_LBO = kAMN ? GEMM_BK * 128 : 0;
       constexpr uint32_t B_LBO = kBMN ? GEMM_BK * 128 : 0;
@@ -178,7 +205,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t b_desc = make_smem_desc_sw128(b_addr + k * B_KSTEP, B_LBO, 1024);
             umma_bf16_ss<kCG>(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if constexpr (kCG == 1) umma_commit(&empty[stage]); else umma_commit_2sm(&empty[stage], 0x3);
+          if constexpr (kMode == 1) umma_commit(&empty[stage]);
+          else if constexpr (kMode == 2) umma_commit_2sm(&empty[stage], 0x3);
+          else umma_commit_mc(&empty[stage], 0x3);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -201,7 +230,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int acc_stage = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const long long row_base =
-          static_cast<long long>(tc.m_blk) * (GEMM_BM_CTA * kCG) + cta_rank * GEMM_BM_CTA + q * 32;
+          static_cast<long long>(tc.m_blk) * (GEMM_BM_CTA * kCluster) + cta_rank * GEMM_BM_CTA + q * 32;
       mbar_wait(&tfull[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * GEMM_BN;
@@ -216,7 +245,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   tc_fence_before();
-  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
+  if constexpr (kCluster == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc<kCG>(tmem_base, 512);
@@ -248,10 +277,11 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, __nv_bfl
   }
 }
 
-template <int kCG, bool kAMN, bool kBMN>
+template <int kMode, bool kAMN, bool kBMN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<kCG>;
-  auto kern = gemm_bf16_kernel<kCG, kAMN, kBMN>;
+  using Cfg = GemmCfg<kMode>;
+  constexpr int kCG = Cfg::CLUSTER;  // CTAs per cluster
+  auto kern = gemm_bf16_kernel<kMode, kAMN, kBMN>;
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -297,7 +327,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   return OBT_OK;
 }
 
-static int g_force_cta_group = 0;  // 0 = auto, 1 or 2 = forced (tests / ablations)
+static int g_force_cta_group = 0;  // 0 = auto, 1 / 2 / 3 = forced kernel mode (tests / ablations)
+static int g_auto_mode = 1;        // what "auto" resolves to
 
 }  // namespace obt
 
@@ -330,8 +361,11 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   int cg = g_force_cta_group;
   // auto: one CTA per SM with 128x256 tiles measured 1.17-1.40 PFLOP/s on the block/head shapes (86-95 % of cuBLAS);
   // the CTA-pair variant stays selectable for ablations (obt_gemm_set_cta_group).
-  if (cg == 0) cg = 1;
-  const int bm = GEMM_BM_CTA * cg;
+  // mode 3 = cluster of two such CTAs sharing (multicasting) the B tile.
+  if (cg == 0) cg = g_auto_mode;
+  if (cg == 3 && M <= GEMM_BM_CTA) cg = 1;  // a single row block has no partner to share B with
+  const int cluster = (cg == 1) ? 1 : 2;     // 128-row blocks per tile / CTAs per cluster
+  const int bm = GEMM_BM_CTA * cluster;
 
   GemmParams p = {};
   p.M = static_cast<int>(M);
@@ -359,7 +393,7 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   // split-K when the output tile grid cannot fill the machine and the reduction is long (wgrad shapes).
   p.splits = 1;
   const int tiles = p.num_m * p.num_n;
-  const int slots = sm_count() / cg;
+  const int slots = sm_count() / cluster;
   const bool splittable = (epilogue == EPI_PLAIN || (epilogue == EPI_RESID && aux_in == D && ld_aux_in == ldd)) &&
                           workspace != nullptr && (M * N) % 4 == 0 && (N % 4 == 0) && (ldd % 4 == 0);
   if (splittable && tiles * 2 <= slots && p.num_kb >= 16) {
@@ -383,7 +417,7 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
 
   CUtensorMap tmA, tmB;
   int rc;
-  const int bnl = GEMM_BN / cg;
+  const int bnl = GEMM_BN / cluster;  // B rows per TMA box: modes 2 and 3 load half of the tile per CTA
   if (!a_mn_major) {
     OBT_REQUIRE(lda % 8 == 0, "obt_gemm_bf16: lda=%lld must be a multiple of 8 elements", lda);
     rc = get_tensor_map_2d(&tmA, A, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda), 64,
@@ -415,7 +449,11 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   OBT_LAUNCH(2, false, false)
   OBT_LAUNCH(2, false, true)
   OBT_LAUNCH(2, true, false)
-  OBT_LAUNCH(2, true, true) {
+  OBT_LAUNCH(2, true, true)
+  OBT_LAUNCH(3, false, false)
+  OBT_LAUNCH(3, false, true)
+  OBT_LAUNCH(3, true, false)
+  OBT_LAUNCH(3, true, true) {
     set_last_error("obt_gemm_bf16: no kernel for cta_group=%d", cg);
     rc = OBT_ERR_UNSUPPORTED;
   }

@@ -41,7 +41,7 @@ SHAPES = [(128, 256, 64), (256, 512, 128), (384, 256, 512), (300, 520, 200), (10
 LAYOUTS = [(False, False), (False, True), (True, True), (True, False)]
 
 
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 3])  # 1 CTA / cta_group::2 pair / 2-CTA cluster with multicast B
 @pytest.mark.parametrize("a_mn,b_mn", LAYOUTS)
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_gemm_plain(cg, a_mn, b_mn, M, N, K):
@@ -60,7 +60,7 @@ def test_gemm_plain(cg, a_mn, b_mn, M, N, K):
         lib.obt_gemm_set_cta_group(0)
 
 
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 3])  # 1 CTA / cta_group::2 pair / 2-CTA cluster with multicast B
 def test_gemm_strided_operands_and_output(cg):
     lib, ops = _ops()
     lib.obt_gemm_set_cta_group(cg)
@@ -78,7 +78,7 @@ def test_gemm_strided_operands_and_output(cg):
         lib.obt_gemm_set_cta_group(0)
 
 
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 3])  # 1 CTA / cta_group::2 pair / 2-CTA cluster with multicast B
 def test_gemm_epilogues(cg):
     lib, ops = _ops()
     lib.obt_gemm_set_cta_group(cg)
@@ -109,7 +109,7 @@ def test_gemm_epilogues(cg):
         lib.obt_gemm_set_cta_group(0)
 
 
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 3])  # 1 CTA / cta_group::2 pair / 2-CTA cluster with multicast B
 def test_gemm_splitk_wgrad_shape(cg):
     lib, ops = _ops()
     lib.obt_gemm_set_cta_group(cg)
