@@ -470,68 +470,93 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const long long bh = static_cast<long long>(b) * p.H + h;
     const bool use_drop = p.drop_p > 0.f;
     const float keep_scale = use_drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    const uint32_t drop_thr = static_cast<uint32_t>(ceilf(p.drop_p * 16777216.0f));  // == (u01 >= p) on 24-bit u01
     const int ct = threadIdx.x - 64;  // 0..255 among the compute threads
+    // Per-query parameters are software-pipelined: the global loads for the NEXT relevant sub-tile are issued before
+    // the math of the current one and written to the other smem buffer afterwards, so their latency never sits on
+    // the critical path (the un-pipelined version stalled all 8 warps ~1 us per sub-tile at the barrier).
+    const int qi = ct & 63, quarter = ct >> 6;
+    struct QParams { int lo, hi; float sc, off, ls2, dl; };
+    auto load_params = [&](int it) -> QParams {
+      QParams z;
+      z.lo = 0; z.hi = 0; z.sc = p.scale; z.off = 0.f; z.ls2 = 0.f; z.dl = 0.f;  // query beyond T: contributes nothing
+      const int i = it * 64 + qi;
+      if (ct < 64 && i < T) {
+        z.lo = 0; z.hi = T;
+        if (p.row_lo != nullptr) {
+          z.lo = p.row_lo[static_cast<long long>(b) * T + i];
+          z.hi = p.row_hi[static_cast<long long>(b) * T + i];
+          if (z.lo >= z.hi) { z.lo = 0; z.hi = T; z.sc = 0.f; }
+        }
+        z.off = p.lse[2 * (bh * T + i)];
+        z.ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
+        z.dl = p.delta[bh * T + i];
+      }
+      return z;
+    };
+    auto store_params = [&](int buf, int it, const QParams& z) {
+      float4* c_p = reinterpret_cast<float4*>(sCol + buf * ATT_COL_STRIDE);  // {scale*log2e, (max+lsum)*log2e, delta, scale}
+      int2* c_lh = reinterpret_cast<int2*>(c_p + 64);                        // {lo, hi}
+      float2* c_x = reinterpret_cast<float2*>(c_lh + 64);                    // {max (natural), lsum*log2e} (dense path)
+      uint32_t* c_keep = reinterpret_cast<uint32_t*>(c_x + 64);              // [64 queries][4 words] dropout keep bits
+      int2* c_rng = reinterpret_cast<int2*>(c_keep + 256);                   // per 32-query chunk: {max lo, min hi}
+      if (ct < 64) {
+        c_p[qi] = make_float4(z.sc * LOG2E, z.off * LOG2E + z.ls2, z.dl, z.sc);
+        c_lh[qi] = make_int2(z.lo, z.hi);
+        c_x[qi] = make_float2(z.off, z.ls2);
+        // threads 0..63 are exactly two warps, one per 32-query chunk: interval common to the whole chunk
+        int mlo = z.lo, mhi = z.hi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          mlo = max(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
+          mhi = min(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
+        }
+        if ((ct & 31) == 0) c_rng[ct >> 5] = make_int2(mlo, mhi);
+      }
+      if (use_drop) {  // all 256 threads: keep bits of query qi for keys [32*quarter, +32)
+        uint32_t bits = 0u;
+        const int i = it * 64 + qi;
+        if (i < T) {
+          const unsigned long long e0 =
+              (static_cast<unsigned long long>(bh) * T + i) * T + static_cast<unsigned long long>(j0 + quarter * 32);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint4 rnd = rand4x32(p.seed, (e0 >> 2) + g, p.offset);
+            uint32_t nib = 0;
+            nib |= ((rnd.x >> 8) >= drop_thr) ? 1u : 0u;
+            nib |= ((rnd.y >> 8) >= drop_thr) ? 2u : 0u;
+            nib |= ((rnd.z >> 8) >= drop_thr) ? 4u : 0u;
+            nib |= ((rnd.w >> 8) >= drop_thr) ? 8u : 0u;
+            bits |= nib << (g * 4);
+          }
+        }
+        c_keep[qi * 4 + quarter] = bits;
+      }
+    };
+    auto next_relevant = [&](int it) -> int {
+      ++it;
+      while (it < nq && !relevant(it)) ++it;
+      return it;
+    };
+
     int n = 0;
-    for (int it = 0; it < nq; ++it) {
-      if (!relevant(it)) continue;
+    int it = next_relevant(-1);
+    if (it < nq) {
+      const QParams z0 = load_params(it);
+      store_params(0, it, z0);
+    }
+    compute_bar_sync256();
+    while (it < nq) {
       const int st = n & 1;
       const int i0 = it * 64;
-      float4* c_p = reinterpret_cast<float4*>(sCol + st * ATT_COL_STRIDE);  // {scale*log2e, (max+lsum)*log2e, delta, scale}
-      int2* c_lh = reinterpret_cast<int2*>(c_p + 64);                       // {lo, hi}
-      float2* c_x = reinterpret_cast<float2*>(c_lh + 64);                   // {max (natural), lsum*log2e} (dense path)
-      uint32_t* c_keep = reinterpret_cast<uint32_t*>(c_x + 64);             // [64 queries][4 words] dropout keep bits
-      int2* c_rng = reinterpret_cast<int2*>(c_keep + 256);                  // per 32-query chunk: {max lo, min hi}
-      // parameters of the 64 queries (threads 0..63) and dropout keep bits (all 256 threads: query ct&63, keys
-      // [32*(ct>>6), +32)); the buffer was last read two sub-tiles ago, separated by the barrier of the previous one
-      {
-        const int qi = ct & 63, quarter = ct >> 6;
-        const int i = i0 + qi;
-        if (ct < 64) {
-          int lo = 0, hi = 0;  // query beyond the sequence: contributes nothing
-          float sc = p.scale, off = 0.f, ls2 = 0.f, dl = 0.f;
-          if (i < T) {
-            lo = 0; hi = T;
-            if (p.row_lo != nullptr) {
-              lo = p.row_lo[static_cast<long long>(b) * T + i];
-              hi = p.row_hi[static_cast<long long>(b) * T + i];
-              if (lo >= hi) { lo = 0; hi = T; sc = 0.f; }
-            }
-            off = p.lse[2 * (bh * T + i)];
-            ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
-            dl = p.delta[bh * T + i];
-          }
-          c_p[qi] = make_float4(sc * LOG2E, off * LOG2E + ls2, dl, sc);
-          c_lh[qi] = make_int2(lo, hi);
-          c_x[qi] = make_float2(off, ls2);
-          // threads 0..63 are exactly two warps, one per 32-query chunk: interval common to the whole chunk
-          int mlo = lo, mhi = hi;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            mlo = max(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
-            mhi = min(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
-          }
-          if ((ct & 31) == 0) c_rng[ct >> 5] = make_int2(mlo, mhi);
-        }
-        if (use_drop) {
-          uint32_t bits = 0u;
-          if (i < T) {
-            const unsigned long long e0 =
-                (static_cast<unsigned long long>(bh) * T + i) * T + static_cast<unsigned long long>(j0 + quarter * 32);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const uint4 rnd = rand4x32(p.seed, (e0 >> 2) + g, p.offset);
-              uint32_t nib = 0;
-              nib |= ((rnd.x >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 1u : 0u;
-              nib |= ((rnd.y >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 2u : 0u;
-              nib |= ((rnd.z >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 4u : 0u;
-              nib |= ((rnd.w >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 8u : 0u;
-              bits |= nib << (g * 4);
-            }
-          }
-          c_keep[qi * 4 + quarter] = bits;
-        }
-      }
-      compute_bar_sync256();
+      const int nx = next_relevant(it);
+      QParams zn;
+      if (nx < nq) zn = load_params(nx);  // in flight during the math below
+      const float4* c_p = reinterpret_cast<const float4*>(sCol + st * ATT_COL_STRIDE);
+      const int2* c_lh = reinterpret_cast<const int2*>(c_p + 64);
+      const float2* c_x = reinterpret_cast<const float2*>(c_lh + 64);
+      const uint32_t* c_keep = reinterpret_cast<const uint32_t*>(c_x + 64);
+      const int2* c_rng = reinterpret_cast<const int2*>(c_keep + 256);
       mbar_wait(&sdp_full[st], (n >> 1) & 1);
       tc_fence_after();
       if (n >= 2) mbar_wait(&done[st], ((n >> 1) - 1) & 1);  // P^T / dS^T buffers consumed by sub-tile n-2
@@ -585,6 +610,11 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full[st]);
+      // parameters of the next sub-tile into the other buffer (last read during sub-tile n-1, before the barrier
+      // that ended that iteration)
+      if (nx < nq) store_params(st ^ 1, nx, zn);
+      compute_bar_sync256();
+      it = nx;
       ++n;
     }
     // epilogue: hh = 0 stores dV (TMEM columns 256..383), hh = 1 stores dK (384..511) of this key row
