@@ -332,16 +332,19 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
 constexpr uint32_t ATT_SUB_BYTES = 64 * 128 * 2;  // one [64 rows x 128] bf16 tile = two 8 KB swizzle sub-tiles
 // 64 x float4 + 64 x int2 + 64 x float2 + 256 keep words + 2 x int2, rounded up
 constexpr uint32_t ATT_COL_STRIDE = 3200;
+constexpr int ATT_QDO_STAGES = 3;
 
 struct AttnDkvSmem {
   static constexpr uint32_t K_OFF = 0;
   static constexpr uint32_t V_OFF = K_OFF + ATT_TILE_BYTES;
-  static constexpr uint32_t Q_OFF = V_OFF + ATT_TILE_BYTES;          // 2 stages of 64 queries (16 KB each)
-  static constexpr uint32_t DO_OFF = Q_OFF + 2 * ATT_SUB_BYTES;      // 2 stages
-  static constexpr uint32_t PT_OFF = DO_OFF + 2 * ATT_SUB_BYTES;     // 2 buffers [128 keys x 64 q] (16 KB each)
-  static constexpr uint32_t DST_OFF = PT_OFF + 2 * 16384;            // 2 buffers
+  // 3 TMA stages of 64 queries (16 KB each for Q and for dO): with 2 stages the ~1.5 us TMA round trip was exposed
+  // every other sub-tile (profiles/r01_attn_bwd_v4.details.txt: IPC 0.93, every pipe < 25 %)
+  static constexpr uint32_t Q_OFF = V_OFF + ATT_TILE_BYTES;
+  static constexpr uint32_t DO_OFF = Q_OFF + ATT_QDO_STAGES * ATT_SUB_BYTES;
+  static constexpr uint32_t PT_OFF = DO_OFF + ATT_QDO_STAGES * ATT_SUB_BYTES;  // [128 keys x 64 q] bf16, single buffer
+  static constexpr uint32_t DST_OFF = PT_OFF + 16384;
   // per-query (column) parameters, double buffered (layout: see ATT_COL_STRIDE users in the kernel)
-  static constexpr uint32_t COL_OFF = DST_OFF + 2 * 16384;
+  static constexpr uint32_t COL_OFF = DST_OFF + 16384;
   static constexpr uint32_t BAR_OFF = COL_OFF + 2 * ATT_COL_STRIDE;
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
@@ -360,12 +363,13 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint8_t* sCol = smem + AttnDkvSmem::COL_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnDkvSmem::BAR_OFF);
   uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;  // [2]
-  uint64_t* done = bars + 3;      // [2] dV/dK MMAs of the sub-tile using stage/buffer b completed (frees Q/dO/P^T/dS^T)
-  uint64_t* sdp_full = bars + 5;  // [2]
-  uint64_t* pds_full = bars + 7;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-  unsigned int* s_rel = reinterpret_cast<unsigned int*>(bars + 10);  // relevance bits of the 64-query sub-tiles (<=128)
+  uint64_t* qdo_full = bars + 1;   // [3]
+  uint64_t* qdo_free = bars + 4;   // [3] dV/dK MMAs that read Q/dO stage s completed
+  uint64_t* sdp_full = bars + 7;   // [2]
+  uint64_t* pds_full = bars + 9;   // [2]
+  uint64_t* grad_done = bars + 11; // dV/dK MMAs of a sub-tile completed: P^T / dS^T smem may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  unsigned int* s_rel = reinterpret_cast<unsigned int*>(bars + 13);  // relevance bits of the 64-query sub-tiles (<=128)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j0 = blockIdx.x * ATT_BN;
@@ -378,12 +382,15 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     tma_prefetch_desc(&tm_q64);
     tma_prefetch_desc(&tm_dy64);
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ATT_QDO_STAGES; ++i) {
       mbar_init(&qdo_full[i], 1);
-      mbar_init(&done[i], 1);
+      mbar_init(&qdo_free[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1);
       mbar_init(&pds_full[i], ATT_COMPUTE_WARPS);
     }
+    mbar_init(grad_done, 1);
     fence_barrier_init();
     s_rel[0] = s_rel[1] = s_rel[2] = s_rel[3] = 0;
   }
@@ -418,11 +425,11 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tma_load_2d(&tm_qkv, kv_full, sK + 16384, kcol + 64, row0 + j0);
       tma_load_2d(&tm_qkv, kv_full, sV, vcol, row0 + j0);
       tma_load_2d(&tm_qkv, kv_full, sV + 16384, vcol + 64, row0 + j0);
-      int n = 0;
+      int n = 0, st = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < nq; ++it) {
         if (!relevant(it)) continue;
-        const int st = n & 1;
-        mbar_wait(&done[st], ((n >> 1) & 1) ^ 1);
+        mbar_wait(&qdo_free[st], ph ^ 1);
         mbar_expect_tx(&qdo_full[st], 2 * ATT_SUB_BYTES);
         const int qrow = row0 + it * 64;
         tma_load_2d(&tm_q64, &qdo_full[st], sQ + st * ATT_SUB_BYTES, qcol, qrow);
@@ -430,6 +437,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         tma_load_2d(&tm_dy64, &qdo_full[st], sDO + st * ATT_SUB_BYTES, qcol, qrow);
         tma_load_2d(&tm_dy64, &qdo_full[st], sDO + st * ATT_SUB_BYTES + 8192, qcol + 64, qrow);
         ++n;
+        if (++st == ATT_QDO_STAGES) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -438,26 +446,25 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       int n_total = 0;
       for (int it = 0; it < nq; ++it) n_total += relevant(it) ? 1 : 0;
       mbar_wait(kv_full, 0);
-      auto issue_scores = [&](int n) {
-        const int st = n & 1;
-        mbar_wait(&qdo_full[st], (n >> 1) & 1);
+      auto issue_scores = [&](int n) {  // Q/dO stage n % 3, TMEM score buffer n & 1
+        const int st = n % ATT_QDO_STAGES, tb = n & 1;
+        mbar_wait(&qdo_full[st], (n / ATT_QDO_STAGES) & 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + st * 128;
+        const uint32_t d = tmem_base + tb * 128;
         issue_scores_128x64(d, k_addr, 16384, smem_u32(sQ + st * ATT_SUB_BYTES), 8192);        // S^T  = K Q^T
         issue_scores_128x64(d + 64, v_addr, 16384, smem_u32(sDO + st * ATT_SUB_BYTES), 8192);  // dP^T = V dO^T
-        umma_commit(&sdp_full[st]);
+        umma_commit(&sdp_full[tb]);
       };
       if (n_total > 0) issue_scores(0);
       for (int n = 0; n < n_total; ++n) {
         if (n + 1 < n_total) issue_scores(n + 1);
-        const int st = n & 1;
-        mbar_wait(&pds_full[st], (n >> 1) & 1);
+        const int st = n % ATT_QDO_STAGES, tb = n & 1;
+        mbar_wait(&pds_full[tb], (n >> 1) & 1);
         tc_fence_after();
-        issue_grad_128x128x64(tmem_base + 256, smem_u32(sPT + st * 16384), smem_u32(sDO + st * ATT_SUB_BYTES), 8192,
-                              n > 0);  // dV += P^T dO
-        issue_grad_128x128x64(tmem_base + 384, smem_u32(sDST + st * 16384), smem_u32(sQ + st * ATT_SUB_BYTES), 8192,
-                              n > 0);  // dK += dS^T Q
-        umma_commit(&done[st]);
+        issue_grad_128x128x64(tmem_base + 256, smem_u32(sPT), smem_u32(sDO + st * ATT_SUB_BYTES), 8192, n > 0);   // dV += P^T dO
+        issue_grad_128x128x64(tmem_base + 384, smem_u32(sDST), smem_u32(sQ + st * ATT_SUB_BYTES), 8192, n > 0);  // dK += dS^T Q
+        umma_commit(&qdo_free[st]);
+        umma_commit(grad_done);
       }
     }
   } else {
@@ -559,7 +566,6 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const int2* c_rng = reinterpret_cast<const int2*>(c_keep + 256);
       mbar_wait(&sdp_full[st], (n >> 1) & 1);
       tc_fence_after();
-      if (n >= 2) mbar_wait(&done[st], ((n >> 1) - 1) & 1);  // P^T / dS^T buffers consumed by sub-tile n-2
       uint32_t sv[32], dv[32];
       __syncwarp();
       tmem_ld_32x32(lane_addr + st * 128 + hh * 32, sv);
@@ -594,8 +600,10 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         pt[e] = pr * ks;
         dst[e] = pr * (__uint_as_float(dv[e]) * ks - cp.z) * cp.w;
       }
-      uint8_t* ptb = sPT + st * 16384;
-      uint8_t* dsb = sDST + st * 16384;
+      // the single P^T / dS^T smem tile is free once the dV/dK MMAs of the previous sub-tile have completed
+      if (n >= 1) mbar_wait(grad_done, (n - 1) & 1);
+      uint8_t* ptb = sPT;
+      uint8_t* dsb = sDST;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const uint32_t o = sw128_row64_off(r, hh * 32 + g * 8);
@@ -621,8 +629,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     __nv_bfloat16* dvrow = p.dv + (static_cast<long long>(row0) + j) * p.ldd + h * ATT_D;
     __nv_bfloat16* dkrow = p.dk + (static_cast<long long>(row0) + j) * p.ldd + h * ATT_D;
     if (n > 0) {
-      const int last = n - 1;
-      mbar_wait(&done[last & 1], (last >> 1) & 1);
+      mbar_wait(grad_done, (n - 1) & 1);
       tc_fence_after();
     }
 #pragma unroll 1
