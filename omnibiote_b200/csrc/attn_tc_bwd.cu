@@ -502,13 +502,15 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       return z;
     };
     auto store_params = [&](int buf, int it, const QParams& z) {
-      float4* c_p = reinterpret_cast<float4*>(sCol + buf * ATT_COL_STRIDE);  // {scale*log2e, (max+lsum)*log2e, delta, scale}
-      int2* c_lh = reinterpret_cast<int2*>(c_p + 64);                        // {lo, hi}
-      float2* c_x = reinterpret_cast<float2*>(c_lh + 64);                    // {max (natural), lsum*log2e} (dense path)
-      uint32_t* c_keep = reinterpret_cast<uint32_t*>(c_x + 64);              // [64 queries][4 words] dropout keep bits
-      int2* c_rng = reinterpret_cast<int2*>(c_keep + 256);                   // per 32-query chunk: {max lo, min hi}
+      float2* c_pn = reinterpret_cast<float2*>(sCol + buf * ATT_COL_STRIDE);  // {scale*log2e, (max+lsum)*log2e}
+      float2* c_ds = c_pn + 64;                                               // {delta, scale}
+      int2* c_lh = reinterpret_cast<int2*>(c_ds + 64);                        // {lo, hi}
+      float2* c_x = reinterpret_cast<float2*>(c_lh + 64);                     // {max (natural), lsum*log2e} (dense path)
+      uint32_t* c_keepT = reinterpret_cast<uint32_t*>(c_x + 64);              // [128 keys][2 query halves] keep bits
+      int2* c_rng = reinterpret_cast<int2*>(c_keepT + 256);                   // per 32-query chunk: {max lo, min hi}
       if (ct < 64) {
-        c_p[qi] = make_float4(z.sc * LOG2E, z.off * LOG2E + z.ls2, z.dl, z.sc);
+        c_pn[qi] = make_float2(z.sc * LOG2E, z.off * LOG2E + z.ls2);
+        c_ds[qi] = make_float2(z.dl, z.sc);
         c_lh[qi] = make_int2(z.lo, z.hi);
         c_x[qi] = make_float2(z.off, z.ls2);
         // threads 0..63 are exactly two warps, one per 32-query chunk: interval common to the whole chunk
@@ -520,7 +522,9 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         }
         if ((ct & 31) == 0) c_rng[ct >> 5] = make_int2(mlo, mhi);
       }
-      if (use_drop) {  // all 256 threads: keep bits of query qi for keys [32*quarter, +32)
+      if (use_drop) {
+        // all 256 threads: keep bits of query qi for keys [32*quarter, +32), then transposed with warp ballots so
+        // that the thread owning key k later reads ONE word holding the bits of its 32 query columns
         uint32_t bits = 0u;
         const int i = it * 64 + qi;
         if (i < T) {
@@ -537,7 +541,13 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             bits |= nib << (g * 4);
           }
         }
-        c_keep[qi * 4 + quarter] = bits;
+        // a warp = 32 consecutive queries (one query half) x the same 32-key quarter
+        const int qhalf = (ct & 63) >> 5;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+          const uint32_t w = __ballot_sync(0xffffffffu, (bits >> k) & 1u);
+          if ((ct & 31) == k) c_keepT[(quarter * 32 + k) * 2 + qhalf] = w;
+        }
       }
     };
     auto next_relevant = [&](int it) -> int {
@@ -559,11 +569,12 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const int nx = next_relevant(it);
       QParams zn;
       if (nx < nq) zn = load_params(nx);  // in flight during the math below
-      const float4* c_p = reinterpret_cast<const float4*>(sCol + st * ATT_COL_STRIDE);
-      const int2* c_lh = reinterpret_cast<const int2*>(c_p + 64);
+      const float2* c_pn = reinterpret_cast<const float2*>(sCol + st * ATT_COL_STRIDE);
+      const float2* c_ds = c_pn + 64;
+      const int2* c_lh = reinterpret_cast<const int2*>(c_ds + 64);
       const float2* c_x = reinterpret_cast<const float2*>(c_lh + 64);
-      const uint32_t* c_keep = reinterpret_cast<const uint32_t*>(c_x + 64);
-      const int2* c_rng = reinterpret_cast<const int2*>(c_keep + 256);
+      const uint32_t* c_keepT = reinterpret_cast<const uint32_t*>(c_x + 64);
+      const int2* c_rng = reinterpret_cast<const int2*>(c_keepT + 256);
       mbar_wait(&sdp_full[st], (n >> 1) & 1);
       tc_fence_after();
       uint32_t sv[32], dv[32];
@@ -576,29 +587,37 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       // every key of this warp visible to every query of the chunk (interior of a document): warp-uniform test
       const bool interior = (p.mask == nullptr) && (j0 + q * 32 >= rng.x) && (j0 + q * 32 + 32 <= rng.y) &&
                             (j0 + q * 32 + 32 <= T);
+      // per-column parameters are read two columns per 16-byte shared load; the keep bits of this key for all 32
+      // query columns are one word
+      const uint32_t keep_word = use_drop ? c_keepT[r * 2 + hh] : 0xffffffffu;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const int col = hh * 32 + e;
-        const float4 cp = c_p[col];
-        float pr;
-        if (interior) {
-          pr = fast_exp2(fmaf(__uint_as_float(sv[e]), cp.x, -cp.y));
-        } else if (p.mask != nullptr) {
-          const int i = i0 + col;
-          const float2 cx = c_x[col];
-          const bool vis = key_ok && i < T;
-          const float bias = vis ? __bfloat162float(p.mask[b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq + j]) : 0.f;
-          const float sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
-          pr = vis ? fast_exp2((sp - cx.x) * LOG2E - cx.y) : 0.f;
-        } else {
-          const int2 lh = c_lh[col];
-          const bool vis = key_ok && j >= lh.x && j < lh.y;
-          pr = vis ? fast_exp2(__uint_as_float(sv[e]) * cp.x - cp.y) : 0.f;
+      for (int e2 = 0; e2 < 16; ++e2) {
+        const float4 pn = reinterpret_cast<const float4*>(c_pn)[hh * 16 + e2];  // {sc2, neg} of columns 2*e2, 2*e2+1
+        const float4 dsp = reinterpret_cast<const float4*>(c_ds)[hh * 16 + e2]; // {delta, scale} of the same two
+        const float sc2[2] = {pn.x, pn.z}, neg[2] = {pn.y, pn.w}, dlt[2] = {dsp.x, dsp.z}, scl[2] = {dsp.y, dsp.w};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int e = e2 * 2 + u;
+          const int col = hh * 32 + e;
+          float pr;
+          if (interior) {
+            pr = fast_exp2(fmaf(__uint_as_float(sv[e]), sc2[u], -neg[u]));
+          } else if (p.mask != nullptr) {
+            const int i = i0 + col;
+            const float2 cx = c_x[col];
+            const bool vis = key_ok && i < T;
+            const float bias = vis ? __bfloat162float(p.mask[b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq + j]) : 0.f;
+            const float sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
+            pr = vis ? fast_exp2((sp - cx.x) * LOG2E - cx.y) : 0.f;
+          } else {
+            const int2 lh = c_lh[col];
+            const bool vis = key_ok && j >= lh.x && j < lh.y;
+            pr = vis ? fast_exp2(__uint_as_float(sv[e]) * sc2[u] - neg[u]) : 0.f;
+          }
+          const float ks = ((keep_word >> e) & 1u) ? keep_scale : 0.f;
+          pt[e] = pr * ks;
+          dst[e] = pr * (__uint_as_float(dv[e]) * ks - dlt[u]) * scl[u];
         }
-        float ks = 1.0f;
-        if (use_drop) ks = ((c_keep[col * 4 + q] >> lane) & 1u) ? keep_scale : 0.f;
-        pt[e] = pr * ks;
-        dst[e] = pr * (__uint_as_float(dv[e]) * ks - cp.z) * cp.w;
       }
       // the single P^T / dS^T smem tile is free once the dV/dK MMAs of the previous sub-tile have completed
       if (n >= 1) mbar_wait(grad_done, (n - 1) & 1);
