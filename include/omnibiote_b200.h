@@ -93,28 +93,33 @@ int obt_pool_bwd(const void* emb, const void* pooled, const void* dout, void* de
  * transpose+contiguous of model.py:148 disappears. mask: additive bf16, element (b,h,i,j) at
  * mask[b*msb + h*msh + i*msq + j] (msh = 0 for the head-expanded view of train_encoder.py:292), or NULL.
  * row_lo/row_hi (optional, instead of mask): per (b,i) visible key interval; lo >= hi marks a fully-masked row
- * (uniform attention). lse: fp32 [B,H,T,2] = (row max, log exp-sum). */
+ * (uniform attention). lse: fp32 [B,H,T,2] = (row max, log exp-sum).
+ * Attention dropout (dropout_p of model.py:118,134) is a precomputed bit matrix keep[B,H,T,ceil(T/32)] drawn ONCE
+ * per layer and micro-batch by obt_attn_keep_mask from (seed, offset) and only read by the forward and backward
+ * kernels (key j of query (b,h,i): word j/32, bit 8*(j&3) + 7 - ((j&31)>>2)); keep may be NULL when drop_p == 0. */
+int obt_attn_keep_mask(unsigned int* keep, int B, int H, int T, float drop_p, unsigned long long seed,
+                       unsigned long long offset, cudaStream_t stream);
 int obt_attn_simt_fwd(const void* q, const void* k, const void* v, long long ld, const void* mask, long long msb,
                       long long msh, long long msq, const int* row_lo, const int* row_hi, void* y, long long ldy,
-                      float* lse, int B, int H, int T, int d, float scale, float drop_p, unsigned long long seed,
-                      unsigned long long offset, cudaStream_t stream);
+                      float* lse, int B, int H, int T, int d, float scale, float drop_p, const unsigned int* keep,
+                      cudaStream_t stream);
 int obt_attn_simt_bwd(const void* q, const void* k, const void* v, long long ld, const void* mask, long long msb,
                       long long msh, long long msq, const int* row_lo, const int* row_hi, const void* y, long long ldy,
                       const void* dy, long long lddy, const float* lse, float* delta, void* dq, void* dk, void* dv,
-                      long long ldd, int B, int H, int T, int d, float scale, float drop_p, unsigned long long seed,
-                      unsigned long long offset, cudaStream_t stream);
+                      long long ldd, int B, int H, int T, int d, float scale, float drop_p, const unsigned int* keep,
+                      cudaStream_t stream);
 
 /* tensor-core (tcgen05/TMEM/TMA) forward for head_dim == 128; qkv is the fused [M,3C] buffer (q | k | v). */
 int obt_attn_tc_fwd(const void* qkv, long long ld, const void* mask, long long msb, long long msh, long long msq,
                     const int* row_lo, const int* row_hi, void* y, long long ldy, float* lse, int B, int H, int T, int d,
-                    float scale, float drop_p, unsigned long long seed, unsigned long long offset, cudaStream_t stream);
+                    float scale, float drop_p, const unsigned int* keep, cudaStream_t stream);
 
 /* tensor-core backward (head_dim == 128): delta pre-pass + dQ kernel + dK/dV kernel. dqkv is the fused [M,3C]
  * gradient buffer (dq | dk | dv, pitch ldd); delta is fp32 [B,H,T] scratch; autograd adjoint of model.py:111-148. */
 int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, long long msb, long long msh, long long msq,
                     const int* row_lo, const int* row_hi, const void* y, long long ldy, const void* dy, long long lddy,
                     const float* lse, float* delta, void* dqkv, long long ldd, int B, int H, int T, int d, float scale,
-                    float drop_p, unsigned long long seed, unsigned long long offset, cudaStream_t stream);
+                    float drop_p, const unsigned int* keep, cudaStream_t stream);
 
 /* ---- attention-mask producers / compressors (input contract of the hot path) ------------------------------------
  * obt_doc_mask_intervals : per (b,i) visible key interval [lo,hi) from token ids = create_attention_mask

@@ -7,6 +7,7 @@
 // backward here is the mathematically exact adjoint.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "dropmask.cuh"
 
 namespace obt {
 
@@ -24,7 +25,7 @@ struct AttnSimtParams {
   float* lse;  // [B,H,T,2] = (row max, log of the exp-sum): kept apart so a -1e9 row max cannot absorb log(sum)
   int B, H, T, d;
   float scale, drop_p;
-  unsigned long long seed, offset;
+  const uint32_t* keep;  // dropout keep bits [B,H,T,ceil(T/32)] (dropmask.cuh), required when drop_p > 0
   // backward
   const __nv_bfloat16* dy;
   long long lddy;
@@ -70,10 +71,8 @@ __device__ __forceinline__ float mask_bias(const AttnSimtParams& p, int b, int h
 
 __device__ __forceinline__ float keep_scale(const AttnSimtParams& p, int b, int h, int i, int j) {
   if (p.drop_p <= 0.f) return 1.0f;
-  const unsigned long long e = ((static_cast<unsigned long long>(b) * p.H + h) * p.T + i) * p.T + j;
-  uint4 r = rand4x32(p.seed, e >> 2, p.offset);
-  const uint32_t w = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
-  return ((w >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? 1.0f / (1.0f - p.drop_p) : 0.f;
+  const uint32_t w = p.keep[((static_cast<long long>(b) * p.H + h) * p.T + i) * keep_words(p.T) + (j >> 5)];
+  return ((w >> keep_bit_pos(j & 31)) & 1u) ? 1.0f / (1.0f - p.drop_p) : 0.f;
 }
 
 // grid (ceil(T / warps), H, B); one warp per query row. smem per warp: d floats (q) + T floats (scores).
@@ -240,12 +239,13 @@ using namespace obt;
 
 static int fill_common(AttnSimtParams& p, const void* q, const void* k, const void* v, long long ld, const void* mask,
                        long long msb, long long msh, long long msq, const int* row_lo, const int* row_hi, int B, int H,
-                       int T, int d, float scale, float drop_p, unsigned long long seed, unsigned long long offset) {
+                       int T, int d, float scale, float drop_p, const unsigned int* keep) {
   OBT_REQUIRE(q && k && v, "attention: null q/k/v");
   OBT_REQUIRE(d % 8 == 0 && d > 0, "attention: head_dim=%d must be a positive multiple of 8", d);
   OBT_REQUIRE(ld % 8 == 0, "attention: ld=%lld must be a multiple of 8", ld);
   OBT_REQUIRE(B > 0 && H > 0 && T > 0, "attention: empty problem");
   OBT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "attention: dropout p=%f", drop_p);
+  OBT_REQUIRE(drop_p == 0.f || keep != nullptr, "attention: dropout needs the keep mask (obt_attn_keep_mask)");
   p.q = static_cast<const __nv_bfloat16*>(q);
   p.k = static_cast<const __nv_bfloat16*>(k);
   p.v = static_cast<const __nv_bfloat16*>(v);
@@ -254,17 +254,16 @@ static int fill_common(AttnSimtParams& p, const void* q, const void* k, const vo
   p.msb = msb; p.msh = msh; p.msq = msq;
   p.row_lo = row_lo; p.row_hi = row_hi;
   p.B = B; p.H = H; p.T = T; p.d = d;
-  p.scale = scale; p.drop_p = drop_p; p.seed = seed; p.offset = offset;
+  p.scale = scale; p.drop_p = drop_p; p.keep = keep;
   return OBT_OK;
 }
 
 extern "C" int obt_attn_simt_fwd(const void* q, const void* k, const void* v, long long ld, const void* mask,
                                  long long msb, long long msh, long long msq, const int* row_lo, const int* row_hi,
                                  void* y, long long ldy, float* lse, int B, int H, int T, int d, float scale,
-                                 float drop_p, unsigned long long seed, unsigned long long offset,
-                                 cudaStream_t stream) {
+                                 float drop_p, const unsigned int* keep, cudaStream_t stream) {
   AttnSimtParams p = {};
-  int rc = fill_common(p, q, k, v, ld, mask, msb, msh, msq, row_lo, row_hi, B, H, T, d, scale, drop_p, seed, offset);
+  int rc = fill_common(p, q, k, v, ld, mask, msb, msh, msq, row_lo, row_hi, B, H, T, d, scale, drop_p, keep);
   if (rc) return rc;
   OBT_REQUIRE(y && lse, "obt_attn_simt_fwd: null output");
   p.y = static_cast<__nv_bfloat16*>(y);
@@ -277,10 +276,9 @@ extern "C" int obt_attn_simt_bwd(const void* q, const void* k, const void* v, lo
                                  long long msb, long long msh, long long msq, const int* row_lo, const int* row_hi,
                                  const void* y, long long ldy, const void* dy, long long lddy, const float* lse,
                                  float* delta, void* dq, void* dk, void* dv, long long ldd, int B, int H, int T, int d,
-                                 float scale, float drop_p, unsigned long long seed, unsigned long long offset,
-                                 cudaStream_t stream) {
+                                 float scale, float drop_p, const unsigned int* keep, cudaStream_t stream) {
   AttnSimtParams p = {};
-  int rc = fill_common(p, q, k, v, ld, mask, msb, msh, msq, row_lo, row_hi, B, H, T, d, scale, drop_p, seed, offset);
+  int rc = fill_common(p, q, k, v, ld, mask, msb, msh, msq, row_lo, row_hi, B, H, T, d, scale, drop_p, keep);
   if (rc) return rc;
   OBT_REQUIRE(y && dy && lse && delta && dq && dk && dv, "obt_attn_simt_bwd: null pointer");
   p.y = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(y));

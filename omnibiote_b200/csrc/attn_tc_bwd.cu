@@ -40,37 +40,6 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dy, long lon
   }
 }
 
-// D[128 x 64] = A[128 x 128(d)] * B[64 x 128(d)]^T, both K-major; a tile = two 64-column sub-tiles `a_sub` /
-// `b_sub` bytes apart.
-__device__ __forceinline__ void issue_scores_128x64(uint32_t d_tmem, uint32_t a_addr, uint32_t a_sub, uint32_t b_addr,
-                                                    uint32_t b_sub) {
-  constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, false);
-#pragma unroll
-  for (int kk = 0; kk < 8; ++kk) {
-    const uint64_t a_desc = make_smem_desc_sw128(a_addr + (kk >> 2) * a_sub + (kk & 3) * 32, 0, 1024);
-    const uint64_t b_desc = make_smem_desc_sw128(b_addr + (kk >> 2) * b_sub + (kk & 3) * 32, 0, 1024);
-    umma_bf16_ss<1>(d_tmem, a_desc, b_desc, idesc, kk > 0 ? 1u : 0u);
-  }
-}
-
-// D[128 x 128(d)] += A[128 x 64] * B[64 x 128(d)]: A is a K-major [128 x 64] tile (one 128-byte row per lane),
-// B is read MN-major from a TMA-written [64 rows x 128] tile whose two 64-column halves are `b_lbo` bytes apart.
-__device__ __forceinline__ void issue_grad_128x128x64(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t b_lbo,
-                                                      bool accumulate) {
-  constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, true);
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    const uint64_t a_desc = make_smem_desc_sw128(a_addr + kk * 32, 0, 1024);
-    const uint64_t b_desc = make_smem_desc_sw128(b_addr + kk * 2048, b_lbo, 1024);
-    umma_bf16_ss<1>(d_tmem, a_desc, b_desc, idesc, (accumulate || kk > 0) ? 1u : 0u);
-  }
-}
-
-// byte offset of the 16-byte chunk [c, c+8) of row r in a [128 x 64] bf16 K-major tile (128-byte rows, 128B swizzle)
-__device__ __forceinline__ uint32_t sw128_row64_off(int r, int c) {
-  return static_cast<uint32_t>(r * 128 + (((c >> 3) ^ (r & 7)) << 4));
-}
-
 // =============================================================================================
 // dQ kernel
 // =============================================================================================
@@ -84,6 +53,7 @@ struct AttnDqSmem {
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
 
+template <bool kDrop>
 __global__ void __launch_bounds__(ATT_THREADS_BWD, 1)
 attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dy,
                   const AttnTcParams p, int C) {
@@ -229,13 +199,18 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
     const float sc2 = row_scale * LOG2E;
     const __nv_bfloat16* mrow =
         (p.mask != nullptr && row_ok) ? p.mask + b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq : nullptr;
-    const bool use_drop = p.drop_p > 0.f;
-    const uint32_t drop_thr = static_cast<uint32_t>(ceilf(p.drop_p * 16777216.0f));  // == (u01 >= p) on 24-bit u01
-    const float drop_scale = 1.0f / (1.0f - p.drop_p);
+    // dropout: dP~ = keep o dP / (1-p). The 1/(1-p) is folded: dS' = P o (keep o dP - delta (1-p)) here and
+    // dQ = scale / (1-p) * dS' K in the epilogue.
+    const float inv_keep = kDrop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    const float dlp = kDrop ? dl * (1.0f - p.drop_p) : dl;
+    const uint32_t* keep_row = nullptr;
+    if (kDrop && row_ok) keep_row = p.keep + (bh * T + i) * p.nw;
 
     for (int s = 0; s < n_sub; ++s) {
       const int bsel = s & 1;
       const int j0 = (jb + (s >> 1)) * ATT_BN + (s & 1) * 64 + hh * 32;  // first key of this thread's 32 columns
+      uint32_t kw = 0xffffffffu;
+      if (kDrop && keep_row != nullptr && (j0 >> 5) < p.nw) kw = keep_row[j0 >> 5];
       mbar_wait(&sdp_full[bsel], (s >> 1) & 1);
       tc_fence_after();
       if (s >= 2) mbar_wait(&buf_free[bsel], ((s >> 1) - 1) & 1);  // dS buffer consumed by dQ of sub-tile s-2
@@ -245,7 +220,7 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
       tmem_ld_32x32(lane_addr + bsel * 128 + 64 + hh * 32, dv);
       tmem_ld_wait();
       float ds[32];  // first P, then dS
-      if (p.mask != nullptr) {  // dense additive bias (warp-uniform branch)
+      if (p.mask != nullptr) {  // dense additive bias (kernel-uniform branch)
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const int j = j0 + e;
@@ -266,22 +241,15 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
           ds[e] = (j >= lo && j < hi && row_ok) ? fast_exp2(__uint_as_float(sv[e]) * sc2 - neg) : 0.f;
         }
       }
-      if (use_drop) {
-        const unsigned long long e0 =
-            ((static_cast<unsigned long long>(bh) * T + i) * T) + static_cast<unsigned long long>(j0);
+      if (kDrop) {
 #pragma unroll
-        for (int g4 = 0; g4 < 8; ++g4) {
-          const uint4 rnd = rand4x32(p.seed, (e0 >> 2) + g4, p.offset);
-          const float k0 = ((rnd.x >> 8) >= drop_thr) ? drop_scale : 0.f, k1 = ((rnd.y >> 8) >= drop_thr) ? drop_scale : 0.f;
-          const float k2 = ((rnd.z >> 8) >= drop_thr) ? drop_scale : 0.f, k3 = ((rnd.w >> 8) >= drop_thr) ? drop_scale : 0.f;
-          ds[g4 * 4 + 0] *= (__uint_as_float(dv[g4 * 4 + 0]) * k0 - dl) * row_scale;
-          ds[g4 * 4 + 1] *= (__uint_as_float(dv[g4 * 4 + 1]) * k1 - dl) * row_scale;
-          ds[g4 * 4 + 2] *= (__uint_as_float(dv[g4 * 4 + 2]) * k2 - dl) * row_scale;
-          ds[g4 * 4 + 3] *= (__uint_as_float(dv[g4 * 4 + 3]) * k3 - dl) * row_scale;
+        for (int e = 0; e < 32; ++e) {
+          const float dpk = (kw & (1u << keep_bit_pos(e))) ? __uint_as_float(dv[e]) : 0.f;
+          ds[e] *= dpk - dlp;
         }
       } else {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) ds[e] *= (__uint_as_float(dv[e]) - dl) * row_scale;
+        for (int e = 0; e < 32; ++e) ds[e] *= __uint_as_float(dv[e]) - dlp;
       }
       uint8_t* dsb = sDS + bsel * 16384;
 #pragma unroll
@@ -300,6 +268,7 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
     mbar_wait(&buf_free[last & 1], (last >> 1) & 1);
     tc_fence_after();
     __nv_bfloat16* drow = p.dq + (static_cast<long long>(row0) + i) * p.ldd + h * ATT_D;
+    const float oscale = row_scale * inv_keep;
 #pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
       const int c = hh * 2 + cc;
@@ -311,10 +280,10 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           reinterpret_cast<uint4*>(drow + c * 32)[g] = make_uint4(
-              pack_bf16x2(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1])),
-              pack_bf16x2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3])),
-              pack_bf16x2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5])),
-              pack_bf16x2(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7])));
+              pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * oscale, __uint_as_float(o[g * 8 + 1]) * oscale),
+              pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * oscale, __uint_as_float(o[g * 8 + 3]) * oscale),
+              pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * oscale, __uint_as_float(o[g * 8 + 5]) * oscale),
+              pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * oscale, __uint_as_float(o[g * 8 + 7]) * oscale));
       }
     }
     tc_fence_before();
@@ -330,8 +299,9 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
 // dK / dV kernel
 // =============================================================================================
 constexpr uint32_t ATT_SUB_BYTES = 64 * 128 * 2;  // one [64 rows x 128] bf16 tile = two 8 KB swizzle sub-tiles
-// 64 x float4 + 64 x int2 + 64 x float2 + 256 keep words + 2 x int2, rounded up
-constexpr uint32_t ATT_COL_STRIDE = 3200;
+// per 64-query sub-tile: 64 x float2 {-(max+lsum)*log2e, delta*(1-p)} + 64 x int2 {lo,hi} + 64 x float2 {max, lsum*log2e}
+// + 64 x float live + 4 x 64 keep words + 2 x int4 chunk ranges, rounded up
+constexpr uint32_t ATT_COL_STRIDE = 3072;
 constexpr int ATT_QDO_STAGES = 3;
 
 struct AttnDkvSmem {
@@ -349,6 +319,7 @@ struct AttnDkvSmem {
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
 
+template <bool kDrop>
 __global__ void __launch_bounds__(ATT_THREADS_BWD, 1)
 attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_q64,
                    const __grid_constant__ CUtensorMap tm_dy64, const AttnTcParams p, int C) {
@@ -475,80 +446,63 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const bool key_ok = j < T;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const long long bh = static_cast<long long>(b) * p.H + h;
-    const bool use_drop = p.drop_p > 0.f;
-    const float keep_scale = use_drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
-    const uint32_t drop_thr = static_cast<uint32_t>(ceilf(p.drop_p * 16777216.0f));  // == (u01 >= p) on 24-bit u01
+    const float inv_keep = kDrop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    const float keep_frac = kDrop ? 1.0f - p.drop_p : 1.0f;
+    const float sc2 = p.scale * LOG2E;
+    const uint32_t mybit = 1u << keep_bit_pos(lane);  // this key's bit inside the keep word of its 32-key group
     const int ct = threadIdx.x - 64;  // 0..255 among the compute threads
     // Per-query parameters are software-pipelined: the global loads for the NEXT relevant sub-tile are issued before
     // the math of the current one and written to the other smem buffer afterwards, so their latency never sits on
-    // the critical path (the un-pipelined version stalled all 8 warps ~1 us per sub-tile at the barrier).
-    const int qi = ct & 63, quarter = ct >> 6;
-    struct QParams { int lo, hi; float sc, off, ls2, dl; };
+    // the critical path.
+    struct QParams { int lo, hi; float off, ls2, dl, live; uint32_t kw; };
     auto load_params = [&](int it) -> QParams {
       QParams z;
-      z.lo = 0; z.hi = 0; z.sc = p.scale; z.off = 0.f; z.ls2 = 0.f; z.dl = 0.f;  // query beyond T: contributes nothing
-      const int i = it * 64 + qi;
-      if (ct < 64 && i < T) {
-        z.lo = 0; z.hi = T;
-        if (p.row_lo != nullptr) {
-          z.lo = p.row_lo[static_cast<long long>(b) * T + i];
-          z.hi = p.row_hi[static_cast<long long>(b) * T + i];
-          if (z.lo >= z.hi) { z.lo = 0; z.hi = T; z.sc = 0.f; }
+      z.lo = 0; z.hi = 0; z.off = 0.f; z.ls2 = 0.f; z.dl = 0.f; z.live = 1.f;  // query beyond T: contributes nothing
+      z.kw = 0xffffffffu;
+      if (ct < 64) {
+        const int i = it * 64 + ct;
+        if (i < T) {
+          z.lo = 0; z.hi = T;
+          if (p.row_lo != nullptr) {
+            z.lo = p.row_lo[static_cast<long long>(b) * T + i];
+            z.hi = p.row_hi[static_cast<long long>(b) * T + i];
+            if (z.lo >= z.hi) { z.lo = 0; z.hi = T; z.live = 0.f; }  // fully-masked row: uniform P, no dS
+          }
+          z.off = p.lse[2 * (bh * T + i)];
+          z.ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
+          z.dl = p.delta[bh * T + i] * keep_frac;
         }
-        z.off = p.lse[2 * (bh * T + i)];
-        z.ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
-        z.dl = p.delta[bh * T + i];
+      }
+      if (kDrop) {  // thread ct: query ct >> 2, key word ct & 3 of this 128-key tile
+        const int i = it * 64 + (ct >> 2);
+        const int w = (j0 >> 5) + (ct & 3);
+        if (i < T && w < p.nw) z.kw = p.keep[(bh * T + i) * p.nw + w];
       }
       return z;
     };
-    auto store_params = [&](int buf, int it, const QParams& z) {
-      float2* c_pn = reinterpret_cast<float2*>(sCol + buf * ATT_COL_STRIDE);  // {scale*log2e, (max+lsum)*log2e}
-      float2* c_ds = c_pn + 64;                                               // {delta, scale}
-      int2* c_lh = reinterpret_cast<int2*>(c_ds + 64);                        // {lo, hi}
-      float2* c_x = reinterpret_cast<float2*>(c_lh + 64);                     // {max (natural), lsum*log2e} (dense path)
-      uint32_t* c_keepT = reinterpret_cast<uint32_t*>(c_x + 64);              // [128 keys][2 query halves] keep bits
-      int2* c_rng = reinterpret_cast<int2*>(c_keepT + 256);                   // per 32-query chunk: {max lo, min hi}
+    auto store_params = [&](int buf, const QParams& z) {
+      uint8_t* base = sCol + buf * ATT_COL_STRIDE;
+      float2* c_nd = reinterpret_cast<float2*>(base);          // {-(max + lsum) * log2e, delta * (1-p)}
+      int2* c_lh = reinterpret_cast<int2*>(base + 512);        // {lo, hi}
+      float2* c_x = reinterpret_cast<float2*>(base + 1024);    // {max (natural), lsum * log2e} (dense path)
+      float* c_live = reinterpret_cast<float*>(base + 1536);   // 0 for fully-masked queries
+      uint32_t* c_keep = reinterpret_cast<uint32_t*>(base + 1792);  // [4 key words][64 queries]
+      int4* c_rng = reinterpret_cast<int4*>(base + 2816);      // per 32-query chunk: {max lo, min hi}
       if (ct < 64) {
-        c_pn[qi] = make_float2(z.sc * LOG2E, z.off * LOG2E + z.ls2);
-        c_ds[qi] = make_float2(z.dl, z.sc);
-        c_lh[qi] = make_int2(z.lo, z.hi);
-        c_x[qi] = make_float2(z.off, z.ls2);
+        c_nd[ct] = make_float2(-(z.off * LOG2E + z.ls2), z.dl);
+        c_lh[ct] = make_int2(z.lo, z.hi);
+        c_x[ct] = make_float2(z.off, z.ls2);
+        c_live[ct] = z.live;
         // threads 0..63 are exactly two warps, one per 32-query chunk: interval common to the whole chunk
-        int mlo = z.lo, mhi = z.hi;
+        int mlo = (z.live == 0.f) ? 0x7fffffff : z.lo, mhi = z.hi;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           mlo = max(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
           mhi = min(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
         }
-        if ((ct & 31) == 0) c_rng[ct >> 5] = make_int2(mlo, mhi);
+        if ((ct & 31) == 0) c_rng[ct >> 5] = make_int4(mlo, mhi, 0, 0);
       }
-      if (use_drop) {
-        // all 256 threads: keep bits of query qi for keys [32*quarter, +32), then transposed with warp ballots so
-        // that the thread owning key k later reads ONE word holding the bits of its 32 query columns
-        uint32_t bits = 0u;
-        const int i = it * 64 + qi;
-        if (i < T) {
-          const unsigned long long e0 =
-              (static_cast<unsigned long long>(bh) * T + i) * T + static_cast<unsigned long long>(j0 + quarter * 32);
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const uint4 rnd = rand4x32(p.seed, (e0 >> 2) + g, p.offset);
-            uint32_t nib = 0;
-            nib |= ((rnd.x >> 8) >= drop_thr) ? 1u : 0u;
-            nib |= ((rnd.y >> 8) >= drop_thr) ? 2u : 0u;
-            nib |= ((rnd.z >> 8) >= drop_thr) ? 4u : 0u;
-            nib |= ((rnd.w >> 8) >= drop_thr) ? 8u : 0u;
-            bits |= nib << (g * 4);
-          }
-        }
-        // a warp = 32 consecutive queries (one query half) x the same 32-key quarter
-        const int qhalf = (ct & 63) >> 5;
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-          const uint32_t w = __ballot_sync(0xffffffffu, (bits >> k) & 1u);
-          if ((ct & 31) == k) c_keepT[(quarter * 32 + k) * 2 + qhalf] = w;
-        }
-      }
+      if (kDrop) c_keep[(ct & 3) * 64 + (ct >> 2)] = z.kw;
     };
     auto next_relevant = [&](int it) -> int {
       ++it;
@@ -560,7 +514,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     int it = next_relevant(-1);
     if (it < nq) {
       const QParams z0 = load_params(it);
-      store_params(0, it, z0);
+      store_params(0, z0);
     }
     compute_bar_sync256();
     while (it < nq) {
@@ -569,12 +523,13 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const int nx = next_relevant(it);
       QParams zn;
       if (nx < nq) zn = load_params(nx);  // in flight during the math below
-      const float2* c_pn = reinterpret_cast<const float2*>(sCol + st * ATT_COL_STRIDE);
-      const float2* c_ds = c_pn + 64;
-      const int2* c_lh = reinterpret_cast<const int2*>(c_ds + 64);
-      const float2* c_x = reinterpret_cast<const float2*>(c_lh + 64);
-      const uint32_t* c_keepT = reinterpret_cast<const uint32_t*>(c_x + 64);
-      const int2* c_rng = reinterpret_cast<const int2*>(c_keepT + 256);
+      const uint8_t* base = sCol + st * ATT_COL_STRIDE;
+      const float4* nd4 = reinterpret_cast<const float4*>(base) + hh * 16;               // two queries per float4
+      const int2* c_lh = reinterpret_cast<const int2*>(base + 512) + hh * 32;
+      const float2* c_x = reinterpret_cast<const float2*>(base + 1024) + hh * 32;
+      const float* c_live = reinterpret_cast<const float*>(base + 1536) + hh * 32;
+      const uint4* kp4 = reinterpret_cast<const uint4*>(base + 1792 + (q * 64 + hh * 32) * 4);  // four queries per uint4
+      const int4 rng = reinterpret_cast<const int4*>(base + 2816)[hh];
       mbar_wait(&sdp_full[st], (n >> 1) & 1);
       tc_fence_after();
       uint32_t sv[32], dv[32];
@@ -583,40 +538,69 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tmem_ld_32x32(lane_addr + st * 128 + 64 + hh * 32, dv);
       tmem_ld_wait();
       float pt[32], dst[32];
-      const int2 rng = c_rng[hh];
-      // every key of this warp visible to every query of the chunk (interior of a document): warp-uniform test
+      // every key of this warp visible to every (live) query of the chunk: warp-uniform test
       const bool interior = (p.mask == nullptr) && (j0 + q * 32 >= rng.x) && (j0 + q * 32 + 32 <= rng.y) &&
                             (j0 + q * 32 + 32 <= T);
-      // per-column parameters are read two columns per 16-byte shared load; the keep bits of this key for all 32
-      // query columns are one word
-      const uint32_t keep_word = use_drop ? c_keepT[r * 2 + hh] : 0xffffffffu;
+      if (interior) {
 #pragma unroll
-      for (int e2 = 0; e2 < 16; ++e2) {
-        const float4 pn = reinterpret_cast<const float4*>(c_pn)[hh * 16 + e2];  // {sc2, neg} of columns 2*e2, 2*e2+1
-        const float4 dsp = reinterpret_cast<const float4*>(c_ds)[hh * 16 + e2]; // {delta, scale} of the same two
-        const float sc2[2] = {pn.x, pn.z}, neg[2] = {pn.y, pn.w}, dlt[2] = {dsp.x, dsp.z}, scl[2] = {dsp.y, dsp.w};
+        for (int e4 = 0; e4 < 8; ++e4) {
+          uint4 kk = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+          if (kDrop) kk = kp4[e4];
+          const uint32_t kws[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int e = e2 * 2 + u;
-          const int col = hh * 32 + e;
-          float pr;
-          if (interior) {
-            pr = fast_exp2(fmaf(__uint_as_float(sv[e]), sc2[u], -neg[u]));
-          } else if (p.mask != nullptr) {
-            const int i = i0 + col;
-            const float2 cx = c_x[col];
-            const bool vis = key_ok && i < T;
-            const float bias = vis ? __bfloat162float(p.mask[b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq + j]) : 0.f;
-            const float sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
-            pr = vis ? fast_exp2((sp - cx.x) * LOG2E - cx.y) : 0.f;
-          } else {
-            const int2 lh = c_lh[col];
-            const bool vis = key_ok && j >= lh.x && j < lh.y;
-            pr = vis ? fast_exp2(__uint_as_float(sv[e]) * sc2[u] - neg[u]) : 0.f;
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const float4 nd = nd4[e4 * 2 + h2];
+            const float nneg[2] = {nd.x, nd.z}, dlp[2] = {nd.y, nd.w};
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int e = e4 * 4 + h2 * 2 + u;
+              const float pr = fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nneg[u]));
+              const bool kb = !kDrop || (kws[h2 * 2 + u] & mybit);
+              pt[e] = kb ? pr : 0.f;
+              dst[e] = pr * ((kb ? __uint_as_float(dv[e]) : 0.f) - dlp[u]);
+            }
           }
-          const float ks = ((keep_word >> e) & 1u) ? keep_scale : 0.f;
-          pt[e] = pr * ks;
-          dst[e] = pr * (__uint_as_float(dv[e]) * ks - dlt[u]) * scl[u];
+        }
+      } else if (p.mask == nullptr) {
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {
+          uint4 kk = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+          if (kDrop) kk = kp4[e4];
+          const uint32_t kws[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = e4 * 4 + u;
+            const float2 nd = reinterpret_cast<const float2*>(nd4)[e];
+            const int2 lh = c_lh[e];
+            const float live = c_live[e];
+            const bool vis = key_ok && j >= lh.x && j < lh.y;
+            const float pr = vis ? fast_exp2(fmaf(__uint_as_float(sv[e]) * live, sc2, nd.x)) : 0.f;
+            const bool kb = !kDrop || (kws[u] & mybit);
+            pt[e] = kb ? pr : 0.f;
+            dst[e] = pr * ((kb ? __uint_as_float(dv[e]) : 0.f) - nd.y) * live;
+          }
+        }
+      } else {  // dense additive bias
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {
+          uint4 kk = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+          if (kDrop) kk = kp4[e4];
+          const uint32_t kws[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = e4 * 4 + u;
+            const int i = i0 + hh * 32 + e;
+            const float2 nd = reinterpret_cast<const float2*>(nd4)[e];
+            const float2 cx = c_x[e];
+            const bool vis = key_ok && i < T;
+            const float bias =
+                vis ? __bfloat162float(p.mask[b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq + j]) : 0.f;
+            const float sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
+            const float pr = vis ? fast_exp2((sp - cx.x) * LOG2E - cx.y) : 0.f;
+            const bool kb = !kDrop || (kws[u] & mybit);
+            pt[e] = kb ? pr : 0.f;
+            dst[e] = pr * ((kb ? __uint_as_float(dv[e]) : 0.f) - nd.y);
+          }
         }
       }
       // the single P^T / dS^T smem tile is free once the dV/dK MMAs of the previous sub-tile have completed
@@ -639,14 +623,15 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       if (lane == 0) mbar_arrive(&pds_full[st]);
       // parameters of the next sub-tile into the other buffer (last read during sub-tile n-1, before the barrier
       // that ended that iteration)
-      if (nx < nq) store_params(st ^ 1, nx, zn);
+      if (nx < nq) store_params(st ^ 1, zn);
       compute_bar_sync256();
       it = nx;
       ++n;
     }
-    // epilogue: hh = 0 stores dV (TMEM columns 256..383), hh = 1 stores dK (384..511) of this key row
+    // epilogue: hh = 0 stores dV (TMEM columns 256..383) / (1-p), hh = 1 stores dK (384..511) * scale / (1-p)
     __nv_bfloat16* dvrow = p.dv + (static_cast<long long>(row0) + j) * p.ldd + h * ATT_D;
     __nv_bfloat16* dkrow = p.dk + (static_cast<long long>(row0) + j) * p.ldd + h * ATT_D;
+    const float oscale = hh == 0 ? inv_keep : inv_keep * p.scale;
     if (n > 0) {
       mbar_wait(grad_done, (n - 1) & 1);
       tc_fence_after();
@@ -668,10 +653,10 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           reinterpret_cast<uint4*>(dstp)[g] = make_uint4(
-              pack_bf16x2(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1])),
-              pack_bf16x2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3])),
-              pack_bf16x2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5])),
-              pack_bf16x2(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7])));
+              pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * oscale, __uint_as_float(o[g * 8 + 1]) * oscale),
+              pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * oscale, __uint_as_float(o[g * 8 + 3]) * oscale),
+              pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * oscale, __uint_as_float(o[g * 8 + 5]) * oscale),
+              pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * oscale, __uint_as_float(o[g * 8 + 7]) * oscale));
       }
     }
     tc_fence_before();
@@ -690,15 +675,15 @@ using namespace obt;
 extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, long long msb, long long msh,
                                long long msq, const int* row_lo, const int* row_hi, const void* y, long long ldy,
                                const void* dy, long long lddy, const float* lse, float* delta, void* dqkv, long long ldd,
-                               int B, int H, int T, int d, float scale, float drop_p, unsigned long long seed,
-                               unsigned long long offset, cudaStream_t stream) {
+                               int B, int H, int T, int d, float scale, float drop_p, const unsigned int* keep,
+                               cudaStream_t stream) {
   OBT_REQUIRE(qkv && y && dy && lse && delta && dqkv, "obt_attn_tc_bwd: null pointer");
   OBT_REQUIRE(d == ATT_D, "obt_attn_tc_bwd: head_dim=%d, the tensor-core kernel is specialised for 128", d);
   OBT_REQUIRE(B > 0 && H > 0 && T > 0, "obt_attn_tc_bwd: empty problem");
   OBT_REQUIRE(T <= 128 * 64, "obt_attn_tc_bwd: T=%d exceeds %d", T, 128 * 64);
   OBT_REQUIRE(ld % 8 == 0 && ldy % 8 == 0 && lddy % 8 == 0 && ldd % 8 == 0, "obt_attn_tc_bwd: pitches must be multiples of 8");
   OBT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "obt_attn_tc_bwd: dropout p=%f", drop_p);
-  OBT_REQUIRE(drop_p == 0.f || T % 4 == 0, "obt_attn_tc_bwd: attention dropout needs T %% 4 == 0 (T=%d)", T);
+  OBT_REQUIRE(drop_p == 0.f || keep != nullptr, "obt_attn_tc_bwd: dropout needs the keep mask (obt_attn_keep_mask)");
   const int C = H * d;
   const long long M = static_cast<long long>(B) * T;
   CUtensorMap tm_qkv, tm_dy, tm_q64, tm_dy64;
@@ -730,15 +715,19 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
   p.row_hi = mask ? nullptr : row_hi;
   p.lse = const_cast<float*>(lse);
   p.delta = delta;
-  p.drop_p = drop_p; p.seed = seed; p.offset = offset;
+  p.drop_p = drop_p;
+  p.keep = keep;
+  p.nw = keep_words(T);
   p.dq = static_cast<__nv_bfloat16*>(dqkv);
   p.dk = p.dq + C;
   p.dv = p.dq + 2 * C;
   p.ldd = ldd;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(attn_tc_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDqSmem::BYTES);
-    cudaError_t e2 = cudaFuncSetAttribute(attn_tc_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDkvSmem::BYTES);
+    cudaError_t e1 = cudaFuncSetAttribute(attn_tc_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDqSmem::BYTES);
+    cudaError_t e2 = cudaFuncSetAttribute(attn_tc_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDkvSmem::BYTES);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attn_tc_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDqSmem::BYTES);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(attn_tc_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDkvSmem::BYTES);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
       set_last_error("obt_attn_tc_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
       return OBT_ERR_CUDA;
@@ -746,9 +735,15 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
     attr_set = true;
   }
   dim3 grid((T + ATT_BM - 1) / ATT_BM, H, B);
-  attn_tc_dq_kernel<<<grid, ATT_THREADS_BWD, AttnDqSmem::BYTES, stream>>>(tm_qkv, tm_dy, p, C);
+  if (drop_p > 0.f)
+    attn_tc_dq_kernel<true><<<grid, ATT_THREADS_BWD, AttnDqSmem::BYTES, stream>>>(tm_qkv, tm_dy, p, C);
+  else
+    attn_tc_dq_kernel<false><<<grid, ATT_THREADS_BWD, AttnDqSmem::BYTES, stream>>>(tm_qkv, tm_dy, p, C);
   rc = check_launch("attn_tc_dq");
   if (rc) return rc;
-  attn_tc_dkv_kernel<<<grid, ATT_THREADS_BWD, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
+  if (drop_p > 0.f)
+    attn_tc_dkv_kernel<true><<<grid, ATT_THREADS_BWD, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
+  else
+    attn_tc_dkv_kernel<false><<<grid, ATT_THREADS_BWD, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
   return check_launch("attn_tc_dkv");
 }

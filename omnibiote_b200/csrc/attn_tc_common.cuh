@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
+#include "dropmask.cuh"
 
 namespace obt {
 
@@ -24,7 +25,8 @@ struct AttnTcParams {
   long long ldy;
   float* lse;  // [B,H,T,2] (row max, log exp-sum) in natural-log units of the scaled+biased scores
   float drop_p;
-  unsigned long long seed, offset;
+  const uint32_t* keep;  // dropout keep bits [B,H,T,nw] (dropmask.cuh); required when drop_p > 0
+  int nw;                // words per query row = ceil(T / 32)
   // backward
   const float* delta;  // [B,H,T] = rowsum(dO * O)
   __nv_bfloat16* dq;   // gradients are written into the fused dqkv buffer [M, 3C] (pitch ldd)
@@ -62,14 +64,46 @@ __device__ __forceinline__ void issue_128x128x128(uint32_t d_tmem, uint32_t a_ad
   }
 }
 
-// dropout keep * 1/(1-p) factors for 4 consecutive keys starting at flat element index e0 (e0 % 4 == 0)
-__device__ __forceinline__ void keep4(const AttnTcParams& p, unsigned long long e0, float (&ks)[4]) {
-  const uint4 rnd = rand4x32(p.seed, e0 >> 2, p.offset);
-  const float s = 1.0f / (1.0f - p.drop_p);
-  ks[0] = ((rnd.x >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? s : 0.f;
-  ks[1] = ((rnd.y >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? s : 0.f;
-  ks[2] = ((rnd.z >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? s : 0.f;
-  ks[3] = ((rnd.w >> 8) * (1.0f / 16777216.0f) >= p.drop_p) ? s : 0.f;
+// D[128 x 64] = A[128 x 128(d)] * B[64 x 128(d)]^T, both K-major; a tile = two 64-column sub-tiles `a_sub` /
+// `b_sub` bytes apart.
+__device__ __forceinline__ void issue_scores_128x64(uint32_t d_tmem, uint32_t a_addr, uint32_t a_sub, uint32_t b_addr,
+                                                    uint32_t b_sub) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, false);
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const uint64_t a_desc = make_smem_desc_sw128(a_addr + (kk >> 2) * a_sub + (kk & 3) * 32, 0, 1024);
+    const uint64_t b_desc = make_smem_desc_sw128(b_addr + (kk >> 2) * b_sub + (kk & 3) * 32, 0, 1024);
+    umma_bf16_ss<1>(d_tmem, a_desc, b_desc, idesc, kk > 0 ? 1u : 0u);
+  }
+}
+
+// D[128 x 128(d)] += A[128 x 64] * B[64 x 128(d)]: A is a K-major [128 x 64] tile (one 128-byte row per lane),
+// B is read MN-major from a TMA-written [64 rows x 128] tile whose two 64-column halves are `b_lbo` bytes apart.
+__device__ __forceinline__ void issue_grad_128x128x64(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t b_lbo,
+                                                      bool accumulate) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, true);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const uint64_t a_desc = make_smem_desc_sw128(a_addr + kk * 32, 0, 1024);
+    const uint64_t b_desc = make_smem_desc_sw128(b_addr + kk * 2048, b_lbo, 1024);
+    umma_bf16_ss<1>(d_tmem, a_desc, b_desc, idesc, (accumulate || kk > 0) ? 1u : 0u);
+  }
+}
+
+// Same product with A = bf16 [128 x 64] held in TMEM (32 columns, two keys per 32-bit column, lane = row).
+__device__ __forceinline__ void issue_pv_ts_128x128x64(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, uint32_t b_lbo,
+                                                       bool accumulate) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, true);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const uint64_t b_desc = make_smem_desc_sw128(b_addr + kk * 2048, b_lbo, 1024);
+    umma_bf16_ts(d_tmem, a_tmem + kk * 8, b_desc, idesc, (accumulate || kk > 0) ? 1u : 0u);
+  }
+}
+
+// byte offset of the 16-byte chunk [c, c+8) of row r in a [128 x 64] bf16 K-major tile (128-byte rows, 128B swizzle)
+__device__ __forceinline__ uint32_t sw128_row64_off(int r, int c) {
+  return static_cast<uint32_t>(r * 128 + (((c >> 3) ^ (r & 7)) << 4));
 }
 
 // named barrier among the 256 compute threads (warps 2..9)

@@ -107,7 +107,8 @@ class BlockFunction(torch.autograd.Function):
         h1, _, mean1, rstd1 = ops.layernorm_fwd(x, g1)
         qkv = ops.gemm(h1, w_qkv)
         ops.rope_(qkv, cos_tab, sin_tab, T, C, d)
-        y, lse = ops.attention_fwd(qkv, B, T, H, d, scale, mask, p, *seeds[0])
+        keep = ops.attn_keep_mask(B, H, T, p, *seeds[0], dev) if p > 0.0 else None
+        y, lse = ops.attention_fwd(qkv, B, T, H, d, scale, mask, p, keep)
         if p > 0.0:
             x1 = ops.gemm(y, w_o, epilogue=ops.EPI_RESID_DROPOUT, aux_in=x, drop_p=p, seed=seeds[1][0], offset=seeds[1][1])
         else:
@@ -123,6 +124,7 @@ class BlockFunction(torch.autograd.Function):
         ctx.save_for_backward(x, g1, w_qkv, w_o, g2, w_fc, w_pr, cos_tab, sin_tab, mean1, rstd1, h1, qkv, y, lse, x1,
                               mean2, rstd2, h2, u, g)
         ctx.mask = mask
+        ctx.keep = keep
         ctx.meta = (B, T, H, d, p, seeds, scale)
         ctx.params = (g1, w_qkv, w_o, g2, w_fc, w_pr)
         return x2
@@ -151,7 +153,7 @@ class BlockFunction(torch.autograd.Function):
         d_a = ops.dropout(dx1, p, *seeds[1]) if p > 0.0 else dx1
         dw_o = _wgrad(d_a, y, po)
         dy = ops.gemm(d_a, w_o, b_mn=True)
-        dqkv = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, ctx.mask, p, *seeds[0])
+        dqkv = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, ctx.mask, p, ctx.keep)
         ops.rope_(dqkv, cos_tab, sin_tab, T, C, d, inverse=True)
         dw_qkv = _wgrad(dqkv, h1, pqkv)
         dh1 = ops.gemm(dqkv, w_qkv, b_mn=True)

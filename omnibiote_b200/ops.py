@@ -256,9 +256,32 @@ class MaskSpec:
         self.msq = m.stride(2)
 
 
+def keep_words(T: int) -> int:
+    return (T + 31) // 32
+
+
+def attn_keep_mask(B: int, H: int, T: int, drop_p: float, seed: int, offset: int, device) -> torch.Tensor:
+    """Attention-dropout keep bits [B,H,T,ceil(T/32)] (int32 words, bit layout: csrc/dropmask.cuh) for one layer and
+    micro-batch, drawn once and read by the forward, dQ and dK/dV kernels."""
+    keep = torch.empty((B, H, T, keep_words(T)), dtype=torch.int32, device=device)
+    rc = _lib.load().obt_attn_keep_mask(keep.data_ptr(), B, H, T, float(drop_p), seed, offset, _stream())
+    _lib.check(rc, "obt_attn_keep_mask")
+    return keep
+
+
+def keep_mask_to_bool(keep: torch.Tensor, T: int) -> torch.Tensor:
+    """Unpack the keep bits into a bool [B,H,T,T] tensor (tests / debugging)."""
+    e = torch.arange(32, device=keep.device)
+    pos = 8 * (e & 3) + 7 - (e >> 2)
+    bits = (keep.unsqueeze(-1) >> pos) & 1
+    return bits.flatten(-2)[..., :T].bool()
+
+
 def attention_fwd(qkv: torch.Tensor, B: int, T: int, H: int, d: int, scale: float, mask: MaskSpec, drop_p: float,
-                  seed: int, offset: int, impl: str = "auto"):
-    """qkv [M,3C] (post-rotary) -> (y [M,C], lse [B,H,T,2])."""
+                  keep: torch.Tensor | None = None, impl: str = "auto"):
+    """qkv [M,3C] (post-rotary) -> (y [M,C], lse [B,H,T,2]). keep: attn_keep_mask(...) when drop_p > 0."""
+    if drop_p > 0.0 and keep is None:
+        raise RuntimeError("omnibiote_b200: attention dropout needs the keep mask (ops.attn_keep_mask)")
     qkv, ld = _mat(qkv, "qkv")
     C = H * d
     M = B * T
@@ -273,22 +296,24 @@ def attention_fwd(qkv: torch.Tensor, B: int, T: int, H: int, d: int, scale: floa
     if impl == "auto":
         dense_ok = mask.tensor is None or (T % 8 == 0 and mask.msq % 8 == 0 and mask.msb % 8 == 0 and mask.msh % 8 == 0
                                            and mask.tensor.data_ptr() % 16 == 0)
-        impl = "tc" if (d == 128 and dense_ok and (drop_p == 0.0 or T % 4 == 0)) else "simt"
+        impl = "tc" if (d == 128 and dense_ok) else "simt"
     if impl == "tc":
         rc = lib.obt_attn_tc_fwd(qkv.data_ptr(), ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
                                  _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0, y.data_ptr(), C,
-                                 lse.data_ptr(), B, H, T, d, scale, float(drop_p), seed, offset, _stream())
+                                 lse.data_ptr(), B, H, T, d, scale, float(drop_p), _ptr(keep), _stream())
         _lib.check(rc, "obt_attn_tc_fwd")
         return y, lse
     rc = lib.obt_attn_simt_fwd(q, k, v, ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
                                _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0, y.data_ptr(), C,
-                               lse.data_ptr(), B, H, T, d, scale, float(drop_p), seed, offset, _stream())
+                               lse.data_ptr(), B, H, T, d, scale, float(drop_p), _ptr(keep), _stream())
     _lib.check(rc, "obt_attn_simt_fwd")
     return y, lse
 
 
-def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, seed, offset, impl: str = "auto"):
-    """Returns dqkv [M,3C] (gradient w.r.t. the post-rotary q,k and v)."""
+def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, keep=None, impl: str = "auto"):
+    """Returns dqkv [M,3C] (gradient w.r.t. the post-rotary q,k and v). keep: the forward's keep mask."""
+    if drop_p > 0.0 and keep is None:
+        raise RuntimeError("omnibiote_b200: attention dropout needs the keep mask (ops.attn_keep_mask)")
     qkv, ld = _mat(qkv, "qkv")
     dy, lddy = _mat(dy, "attention dy")
     C = H * d
@@ -302,19 +327,19 @@ def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, se
     if impl == "auto":
         impl = ATTN_IMPL
     if impl == "auto":
-        impl = "tc" if (d == 128 and (drop_p == 0.0 or T % 4 == 0)) else "simt"
+        impl = "tc" if d == 128 else "simt"
     if impl == "tc":
         rc = _lib.load().obt_attn_tc_bwd(qkv.data_ptr(), ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
                                          _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0,
                                          y.data_ptr(), C, dy.data_ptr(), lddy, lse.data_ptr(), delta.data_ptr(),
-                                         dqkv.data_ptr(), 3 * C, B, H, T, d, scale, float(drop_p), seed, offset,
+                                         dqkv.data_ptr(), 3 * C, B, H, T, d, scale, float(drop_p), _ptr(keep),
                                          _stream())
         _lib.check(rc, "obt_attn_tc_bwd")
         return dqkv
     rc = _lib.load().obt_attn_simt_bwd(q, k, v, ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
                                        _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0,
                                        y.data_ptr(), C, dy.data_ptr(), lddy, lse.data_ptr(), delta.data_ptr(), dq, dk,
-                                       dv, 3 * C, B, H, T, d, scale, float(drop_p), seed, offset, _stream())
+                                       dv, 3 * C, B, H, T, d, scale, float(drop_p), _ptr(keep), _stream())
     _lib.check(rc, "obt_attn_simt_bwd")
     return dqkv
 

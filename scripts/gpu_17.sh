@@ -1,0 +1,11 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout -k 10 600 python -m pytest tests/test_attention_tc_gpu.py -q -m gpu -p no:cacheprovider --tb=short -x > gpurun_out/t17a.log 2>&1
+echo "attn tests exit $?"; tail -n 25 gpurun_out/t17a.log
+timeout -k 10 900 python -m pytest tests -q -m gpu -p no:cacheprovider --tb=short --deselect tests/test_attention_tc_gpu.py > gpurun_out/t17b.log 2>&1
+echo "other tests exit $?"; tail -n 8 gpurun_out/t17b.log
+timeout -k 10 600 python bench.py --steps 1 --warmup 3 --global-batch 128 --skip-cpu-baseline > gpurun_out/bench17.log 2>&1; echo "bench exit $?"; tail -n 1 gpurun_out/bench17.log | cut -c1-250
+timeout -k 10 600 python bench.py --steps 1 --warmup 3 --global-batch 32 --skip-cpu-baseline > gpurun_out/bench_plain.log 2>&1 &&
+timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches17.csv python bench.py --steps 1 --warmup 3 --global-batch 32 --skip-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+echo "ncu launches exit $?"

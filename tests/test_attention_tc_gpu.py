@@ -57,12 +57,12 @@ def test_attn_tc_forward(B, T, H, mode):
             if T % 8:
                 pytest.skip("dense bias path needs 16-byte aligned mask rows")
             spec = ops.MaskSpec(mask4, B, H, T)
-    y, lse = ops.attention_fwd(qkv, B, T, H, d, scale, spec, 0.0, 0, 0, impl="tc")
+    y, lse = ops.attention_fwd(qkv, B, T, H, d, scale, spec, 0.0, None, impl="tc")
     torch.cuda.synchronize()
     ref = _ref(qkv, B, T, H, d, scale, mask4)
     err = rel_err(y, ref)
     assert err < 8e-3, (mode, B, T, H, err)
-    y2, lse2 = ops.attention_fwd(qkv, B, T, H, d, scale, spec, 0.0, 0, 0, impl="simt")
+    y2, lse2 = ops.attention_fwd(qkv, B, T, H, d, scale, spec, 0.0, None, impl="simt")
     assert rel_err(y, y2) < 8e-3
     # log-sum-exp bookkeeping agrees with the generic kernel (needed by the backward)
     tot, tot2 = lse[..., 0] + lse[..., 1], lse2[..., 0] + lse2[..., 1]
@@ -89,18 +89,87 @@ def test_attn_tc_backward(B, T, H, mode):
         dense = torch.where((j >= lo.unsqueeze(-1)) & (j < hi.unsqueeze(-1)), 0.0, -1e9).to(BF)
         mask4 = dense.unsqueeze(1).expand(-1, H, -1, -1)
         spec = ops.MaskSpec(None, B, H, T, lo, hi) if mode == "interval" else ops.MaskSpec(mask4, B, H, T)
-    y, lse = ops.attention_fwd(qkv, B, T, H, d, scale, spec, 0.0, 0, 0, impl="tc" if (mode != "dense" or T % 8 == 0) else "simt")
+    y, lse = ops.attention_fwd(qkv, B, T, H, d, scale, spec, 0.0, None, impl="tc" if (mode != "dense" or T % 8 == 0) else "simt")
     dy = torch.randn(B * T, C, device="cuda").to(BF)
     dy = (dy.view(B, T, C) * live.unsqueeze(-1)).reshape(B * T, C).contiguous()
     qr = qkv.float().requires_grad_(True)
     _ref(qr, B, T, H, d, scale, mask4).backward(dy.float())
-    dqkv = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, spec, 0.0, 0, 0, impl="tc")
+    dqkv = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, spec, 0.0, None, impl="tc")
     torch.cuda.synchronize()
     for name, sl in [("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))]:
         err = rel_err(dqkv[:, sl], qr.grad[:, sl])
         assert err < 1.5e-2, (mode, B, T, H, name, err)
-    dqkv2 = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, spec, 0.0, 0, 0, impl="simt")
+    dqkv2 = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, spec, 0.0, None, impl="simt")
     assert rel_err(dqkv, dqkv2) < 1.5e-2
+
+
+def _ref_drop(qkv, B, T, H, d, scale, mask4, keep_bool, p):
+    """fp32 torch restatement of SDPA with an explicit dropout keep mask (dropout on the softmax output)."""
+    C = H * d
+    q, k, v = [t.view(B, T, H, d).transpose(1, 2).float() for t in qkv.float().split(C, dim=1)]
+    s = (q @ k.transpose(-1, -2)) * scale
+    if mask4 is not None:
+        s = s + mask4.float()
+    pr = torch.softmax(s, dim=-1) * keep_bool.float() / (1.0 - p)
+    return (pr @ v).transpose(1, 2).reshape(B * T, C)
+
+
+def test_keep_mask_statistics_and_determinism():
+    from omnibiote_b200 import ops
+    B, H, T, p = 2, 4, 1024, 0.1
+    keep = ops.attn_keep_mask(B, H, T, p, 1234, 0, "cuda")
+    kb = ops.keep_mask_to_bool(keep, T)
+    assert kb.shape == (B, H, T, T)
+    rate = float(kb.float().mean())
+    assert abs(rate - (1 - p)) < 5e-4, rate                      # 8.4 M draws: sigma = 1e-4
+    # per-row and per-column rates (no structure along either axis), adjacent-key correlation
+    assert float((kb.float().mean(-1) - (1 - p)).abs().max()) < 0.06
+    assert float((kb.float().mean(-2) - (1 - p)).abs().max()) < 0.06
+    a, b_ = kb[..., :-1].float() - (1 - p), kb[..., 1:].float() - (1 - p)
+    assert abs(float((a * b_).mean()) / (p * (1 - p))) < 5e-3
+    a, b_ = kb[..., :-1, :].float() - (1 - p), kb[..., 1:, :].float() - (1 - p)
+    assert abs(float((a * b_).mean()) / (p * (1 - p))) < 5e-3
+    assert torch.equal(ops.attn_keep_mask(B, H, T, p, 1234, 0, "cuda"), keep)       # same (seed, offset): replay
+    assert not torch.equal(ops.attn_keep_mask(B, H, T, p, 1234, 4, "cuda"), keep)   # different offset
+    assert not torch.equal(ops.attn_keep_mask(B, H, T, p, 1235, 0, "cuda"), keep)   # different seed
+    for pp in (0.25, 0.5):
+        r = float(ops.keep_mask_to_bool(ops.attn_keep_mask(1, 2, 512, pp, 7, 0, "cuda"), 512).float().mean())
+        assert abs(r - (1 - pp)) < 3e-3, (pp, r)
+
+
+@pytest.mark.parametrize("B,T,H", [(2, 256, 2), (1, 200, 1), (2, 1024, 2)])
+@pytest.mark.parametrize("mode", ["none", "interval"])
+def test_attn_dropout_against_torch_with_the_same_keep_mask(B, T, H, mode):
+    """Forward and backward with dropout, elementwise against an fp32 torch restatement that applies the SAME keep
+    mask (unpacked from the bit matrix the kernels read)."""
+    from omnibiote_b200 import ops
+    d = 128
+    C = H * d
+    scale = 8.0 / C
+    p = 0.1
+    torch.manual_seed(11 + T)
+    qkv = (torch.randn(B * T, 3 * C, device="cuda") * 1.5).to(BF)
+    mask4, spec = None, ops.MaskSpec(None, B, H, T)
+    if mode == "interval":
+        ids = _doc_ids(B, T, T + 5)
+        lo, hi = ops.doc_mask_intervals(ids, 3, False)
+        j = torch.arange(T, device="cuda").view(1, 1, T)
+        dense = torch.where((j >= lo.unsqueeze(-1)) & (j < hi.unsqueeze(-1)), 0.0, -1e9).to(BF)
+        mask4 = dense.unsqueeze(1).expand(-1, H, -1, -1)
+        spec = ops.MaskSpec(None, B, H, T, lo, hi)
+    keep = ops.attn_keep_mask(B, H, T, p, 42, 8, "cuda")
+    kb = ops.keep_mask_to_bool(keep, T)
+    y, lse = ops.attention_fwd(qkv, B, T, H, d, scale, spec, p, keep, impl="tc")
+    qr = qkv.float().requires_grad_(True)
+    ref = _ref_drop(qr, B, T, H, d, scale, mask4, kb, p)
+    assert rel_err(y, ref) < 8e-3
+    dy = torch.randn(B * T, C, device="cuda").to(BF)
+    ref.backward(dy.float())
+    dqkv = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, spec, p, keep, impl="tc")
+    torch.cuda.synchronize()
+    for name, sl in [("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))]:
+        err = rel_err(dqkv[:, sl], qr.grad[:, sl])
+        assert err < 1.5e-2, (mode, B, T, H, name, err)
 
 
 def test_attn_dropout_same_mask_in_both_kernels_and_in_backward():
@@ -111,13 +180,14 @@ def test_attn_dropout_same_mask_in_both_kernels_and_in_backward():
     torch.manual_seed(3)
     qkv = (torch.randn(B * T, 3 * C, device="cuda")).to(BF)
     spec = ops.MaskSpec(None, B, H, T)
-    p, seed, off = 0.25, 99, 8
-    y_tc, lse_tc = ops.attention_fwd(qkv, B, T, H, d, scale, spec, p, seed, off, impl="tc")
-    y_si, lse_si = ops.attention_fwd(qkv, B, T, H, d, scale, spec, p, seed, off, impl="simt")
-    y_nd, _ = ops.attention_fwd(qkv, B, T, H, d, scale, spec, 0.0, 0, 0, impl="tc")
-    assert rel_err(y_tc, y_si) < 1e-2           # identical keep-mask (same Philox indexing) in both kernels
+    p = 0.25
+    keep = ops.attn_keep_mask(B, H, T, p, 99, 8, "cuda")
+    y_tc, lse_tc = ops.attention_fwd(qkv, B, T, H, d, scale, spec, p, keep, impl="tc")
+    y_si, lse_si = ops.attention_fwd(qkv, B, T, H, d, scale, spec, p, keep, impl="simt")
+    y_nd, _ = ops.attention_fwd(qkv, B, T, H, d, scale, spec, 0.0, None, impl="tc")
+    assert rel_err(y_tc, y_si) < 1e-2           # identical keep mask in both kernels
     assert rel_err(y_tc, y_nd) > 5e-2           # and it really drops something
     dy = torch.randn(B * T, C, device="cuda").to(BF)
-    g_tc = ops.attention_bwd(qkv, y_tc, dy, lse_tc, B, T, H, d, scale, spec, p, seed, off, impl="tc")
-    g_si = ops.attention_bwd(qkv, y_si, dy, lse_si, B, T, H, d, scale, spec, p, seed, off, impl="simt")
+    g_tc = ops.attention_bwd(qkv, y_tc, dy, lse_tc, B, T, H, d, scale, spec, p, keep, impl="tc")
+    g_si = ops.attention_bwd(qkv, y_si, dy, lse_si, B, T, H, d, scale, spec, p, keep, impl="simt")
     assert rel_err(g_tc, g_si) < 2e-2

@@ -109,7 +109,7 @@ def test_attention_generic_fwd_bwd(d, T, masked):
         m3[1, :T - 5, :T - 5] = 0  # last 5 rows fully masked -> uniform attention over all keys
         mask4 = m3.to(BF).unsqueeze(1).expand(-1, H, -1, -1)
     spec = ops.MaskSpec(mask4, B, H, T)
-    y, lse = ops.attention_fwd(qkv, B, T, H, d, scale, spec, 0.0, 0, 0, impl="simt")
+    y, lse = ops.attention_fwd(qkv, B, T, H, d, scale, spec, 0.0, None, impl="simt")
     qr = qkv.float().requires_grad_(True)
     ref, _ = _sdpa_ref(qr, B, T, H, d, scale, mask4)
     assert rel_err(y, ref) < 5e-3
@@ -120,7 +120,7 @@ def test_attention_generic_fwd_bwd(d, T, masked):
     if masked:
         dy.view(B, T, C)[1, T - 5:] = 0  # fully-masked rows never carry gradient in the reference
     ref.backward(dy.float())
-    dqkv = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, spec, 0.0, 0, 0, impl="simt")
+    dqkv = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, spec, 0.0, None, impl="simt")
     assert rel_err(dqkv, qr.grad) < 8e-3
 
 
@@ -134,8 +134,8 @@ def test_attention_interval_mask_equals_dense_mask():
     dense = ops.mask_from_intervals(lo, hi)
     qkv = torch.randn(B * T, 3 * C, device="cuda").to(BF)
     y1, _ = ops.attention_fwd(qkv, B, T, H, d, 8.0 / C, ops.MaskSpec(dense.unsqueeze(1).expand(-1, H, -1, -1), B, H, T),
-                              0.0, 0, 0, impl="simt")
-    y2, _ = ops.attention_fwd(qkv, B, T, H, d, 8.0 / C, ops.MaskSpec(None, B, H, T, lo, hi), 0.0, 0, 0, impl="simt")
+                              0.0, None, impl="simt")
+    y2, _ = ops.attention_fwd(qkv, B, T, H, d, 8.0 / C, ops.MaskSpec(None, B, H, T, lo, hi), 0.0, None, impl="simt")
     assert torch.equal(y1, y2)
 
 

@@ -73,12 +73,12 @@ def test_attention_ctx4096_tc_vs_generic():
     C = H * d
     qkv = torch.randn(B * T, 3 * C, device="cuda").to(BF)
     spec = ops.MaskSpec(None, B, H, T)
-    y1, l1 = ops.attention_fwd(qkv, B, T, H, d, 8.0 / 1024, spec, 0.0, 0, 0, impl="tc")
-    y2, l2 = ops.attention_fwd(qkv, B, T, H, d, 8.0 / 1024, spec, 0.0, 0, 0, impl="simt")
+    y1, l1 = ops.attention_fwd(qkv, B, T, H, d, 8.0 / 1024, spec, 0.0, None, impl="tc")
+    y2, l2 = ops.attention_fwd(qkv, B, T, H, d, 8.0 / 1024, spec, 0.0, None, impl="simt")
     assert rel_err(y1, y2) < 8e-3
     dy = torch.randn(B * T, C, device="cuda").to(BF)
-    g1 = ops.attention_bwd(qkv, y1, dy, l1, B, T, H, d, 8.0 / 1024, spec, 0.0, 0, 0, impl="tc")
-    g2 = ops.attention_bwd(qkv, y2, dy, l2, B, T, H, d, 8.0 / 1024, spec, 0.0, 0, 0, impl="simt")
+    g1 = ops.attention_bwd(qkv, y1, dy, l1, B, T, H, d, 8.0 / 1024, spec, 0.0, None, impl="tc")
+    g2 = ops.attention_bwd(qkv, y2, dy, l2, B, T, H, d, 8.0 / 1024, spec, 0.0, None, impl="simt")
     assert rel_err(g1, g2) < 1.5e-2
 
 
