@@ -41,39 +41,43 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dy, long lon
 }
 
 // =============================================================================================
-// dQ kernel
+// dQ kernel (v6). profiles/r01_attn_v6_bwd.source.txt showed v5 bound by shared-memory operand fetch: every 64-key
+// sub-tile re-read the Q and dO tiles (A operands, 32 KB each) from smem: 128 KB per sub-tile = 1024 cycles at
+// 128 B/clk against 768 cycles of MMA. Now Q, dO AND dS are TMEM A operands:
+//   TMEM  [0,128) / [128,256)  score buffers: S (64 columns) | dP (64 columns), ping-pong
+//         [256,384)            dQ accumulator
+//         [384,448) [448,512)  Q and dO as bf16 (two d per column), written once by the compute threads straight
+//                              from global memory (no TMA, no smem tile)
+//   dS is written back as bf16 over the S columns its thread has just read and consumed from there by dQ += dS K.
+// Shared memory only holds K/V tiles (3 stages): 48 KB of operand fetch per sub-tile.
 // =============================================================================================
+constexpr int ATT_DQ_KV_STAGES = 3;
+
 struct AttnDqSmem {
-  static constexpr uint32_t Q_OFF = 0;
-  static constexpr uint32_t DO_OFF = Q_OFF + ATT_TILE_BYTES;
-  static constexpr uint32_t K_OFF = DO_OFF + ATT_TILE_BYTES;      // 2 stages of 128 keys
-  static constexpr uint32_t V_OFF = K_OFF + 2 * ATT_TILE_BYTES;   // 2 stages
-  static constexpr uint32_t DS_OFF = V_OFF + 2 * ATT_TILE_BYTES;  // 2 buffers of [128 x 64] (16 KB each)
-  static constexpr uint32_t BAR_OFF = DS_OFF + ATT_TILE_BYTES;
+  static constexpr uint32_t K_OFF = 0;                                           // stages of 128 keys
+  static constexpr uint32_t V_OFF = K_OFF + ATT_DQ_KV_STAGES * ATT_TILE_BYTES;
+  static constexpr uint32_t BAR_OFF = V_OFF + ATT_DQ_KV_STAGES * ATT_TILE_BYTES;
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
 
 template <bool kDrop>
 __global__ void __launch_bounds__(ATT_THREADS_BWD, 1)
-attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dy,
-                  const AttnTcParams p, int C) {
+attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16* __restrict__ qkv, long long ld,
+                  const __nv_bfloat16* __restrict__ dy, long long lddy, const AttnTcParams p, int C) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem + AttnDqSmem::Q_OFF;
-  uint8_t* sDO = smem + AttnDqSmem::DO_OFF;
   uint8_t* sK = smem + AttnDqSmem::K_OFF;
   uint8_t* sV = smem + AttnDqSmem::V_OFF;
-  uint8_t* sDS = smem + AttnDqSmem::DS_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnDqSmem::BAR_OFF);
-  uint64_t* qdo_full = bars + 0;
-  uint64_t* k_full = bars + 1;     // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* v_full = bars + 5;     // [2]
-  uint64_t* sdp_full = bars + 7;   // [2]
-  uint64_t* ds_full = bars + 9;    // [2]
-  uint64_t* buf_free = bars + 11;  // [2]  dQ MMA of the sub-tile that used score/dS buffer b has completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-  int* s_range = reinterpret_cast<int*>(bars + 14);
+  uint64_t* qdo_ready = bars + 0;  // Q / dO are in TMEM (8 compute warps)
+  uint64_t* k_full = bars + 1;     // [3]
+  uint64_t* v_full = bars + 4;     // [3]
+  uint64_t* kv_empty = bars + 7;   // [3]
+  uint64_t* sdp_full = bars + 10;  // [2]
+  uint64_t* ds_full = bars + 12;   // [2]
+  uint64_t* dq_done = bars + 14;   // last dQ MMA completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  int* s_range = reinterpret_cast<int*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.x * ATT_BM;
@@ -82,16 +86,17 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
-    tma_prefetch_desc(&tm_dy);
-    mbar_init(qdo_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    mbar_init(qdo_ready, ATT_COMPUTE_WARPS);
+    for (int i = 0; i < ATT_DQ_KV_STAGES; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1);
       mbar_init(&ds_full[i], ATT_COMPUTE_WARPS);
-      mbar_init(&buf_free[i], 1);
     }
+    mbar_init(dq_done, 1);
     fence_barrier_init();
     s_range[0] = T;
     s_range[1] = 0;
@@ -121,58 +126,57 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
   const int n_tiles = je - jb;   // 128-key tiles
   const int n_sub = 2 * n_tiles;  // 64-key sub-tiles
   const int row0 = b * T;
-  const int qcol = h * ATT_D, kcol = C + h * ATT_D, vcol = 2 * C + h * ATT_D;
+  const int kcol = C + h * ATT_D, vcol = 2 * C + h * ATT_D;
+  constexpr uint32_t TM_DQ = 256, TM_Q = 384, TM_DO = 448;
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(qdo_full, 2 * ATT_TILE_BYTES);
-      tma_load_2d(&tm_qkv, qdo_full, sQ, qcol, row0 + t0);
-      tma_load_2d(&tm_qkv, qdo_full, sQ + 16384, qcol + 64, row0 + t0);
-      tma_load_2d(&tm_dy, qdo_full, sDO, qcol, row0 + t0);
-      tma_load_2d(&tm_dy, qdo_full, sDO + 16384, qcol + 64, row0 + t0);
+      int st = 0;
+      uint32_t ph = 0;
       for (int jj = 0; jj < n_tiles; ++jj) {
-        const int st = jj & 1;
-        const uint32_t par = (jj >> 1) & 1;
         const int krow = row0 + (jb + jj) * ATT_BN;
-        mbar_wait(&kv_empty[st], par ^ 1);
+        mbar_wait(&kv_empty[st], ph ^ 1);
         mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
         tma_load_2d(&tm_qkv, &k_full[st], sK + st * ATT_TILE_BYTES, kcol, krow);
         tma_load_2d(&tm_qkv, &k_full[st], sK + st * ATT_TILE_BYTES + 16384, kcol + 64, krow);
         mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
         tma_load_2d(&tm_qkv, &v_full[st], sV + st * ATT_TILE_BYTES, vcol, krow);
         tma_load_2d(&tm_qkv, &v_full[st], sV + st * ATT_TILE_BYTES + 16384, vcol + 64, krow);
+        if (++st == ATT_DQ_KV_STAGES) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), ds_addr = smem_u32(sDS);
-      mbar_wait(qdo_full, 0);
+      mbar_wait(qdo_ready, 0);
       // scores of sub-tile s: S -> buffer (s&1) columns [0,64), dP -> columns [64,128)
       auto issue_scores = [&](int s) {
-        const int jj = s >> 1, hsub = s & 1, st = jj & 1;
+        const int jj = s >> 1, hsub = s & 1, st = jj % ATT_DQ_KV_STAGES;
         if (hsub == 0) {
-          mbar_wait(&k_full[st], (jj >> 1) & 1);
-          mbar_wait(&v_full[st], (jj >> 1) & 1);
+          const uint32_t ph = (jj / ATT_DQ_KV_STAGES) & 1;
+          mbar_wait(&k_full[st], ph);
+          mbar_wait(&v_full[st], ph);
         }
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES) + hsub * 8192;
         const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES) + hsub * 8192;
         const uint32_t d = tmem_base + (s & 1) * 128;
-        issue_scores_128x64(d, q_addr, 16384, k_addr, 16384);
-        issue_scores_128x64(d + 64, do_addr, 16384, v_addr, 16384);
+        issue_scores_ts_128x64(d, tmem_base + TM_Q, k_addr, 16384);        // S  = Q K^T
+        issue_scores_ts_128x64(d + 64, tmem_base + TM_DO, v_addr, 16384);  // dP = dO V^T
         umma_commit(&sdp_full[s & 1]);
       };
       issue_scores(0);
       for (int s = 0; s < n_sub; ++s) {
-        if (s + 1 < n_sub) issue_scores(s + 1);  // buffer (s+1)&1 was drained before dQ(s-1) was issued
-        const int jj = s >> 1, hsub = s & 1, st = jj & 1;
+        // S(s+1) overwrites the buffer dQ(s-1) read its dS from: MMAs execute in issue order
+        if (s + 1 < n_sub) issue_scores(s + 1);
+        const int jj = s >> 1, hsub = s & 1, st = jj % ATT_DQ_KV_STAGES;
         mbar_wait(&ds_full[s & 1], (s >> 1) & 1);
         tc_fence_after();
         const uint32_t k_rows = smem_u32(sK + st * ATT_TILE_BYTES) + hsub * 8192;  // key rows 64*hsub .. of the tile
-        issue_grad_128x128x64(tmem_base + 256, ds_addr + (s & 1) * 16384, k_rows, 16384, s > 0);  // dQ += dS K
-        umma_commit(&buf_free[s & 1]);
+        const uint32_t dsb = tmem_base + (s & 1) * 128;
+        issue_grad_ts_128x128x64(tmem_base + TM_DQ, dsb, dsb + 32, k_rows, 16384, s > 0);  // dQ += dS K
         if (hsub == 1) umma_commit(&kv_empty[st]);
       }
+      umma_commit(dq_done);
     }
   } else {
     const int q = warp & 3;
@@ -181,6 +185,29 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
     const int i = t0 + r;
     const bool row_ok = i < T;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    // ---- Q and dO rows -> TMEM (this thread: d columns [64*hh, +64) = 32 packed words of each)
+    {
+      uint32_t w[32];
+      const uint4* src = reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(row0) + i) * ld + h * ATT_D + hh * 64);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 u = row_ok ? src[g] : make_uint4(0, 0, 0, 0);
+        w[g * 4 + 0] = u.x; w[g * 4 + 1] = u.y; w[g * 4 + 2] = u.z; w[g * 4 + 3] = u.w;
+      }
+      __syncwarp();
+      tmem_st_32x32(lane_addr + TM_Q + hh * 32, w);
+      const uint4* src2 = reinterpret_cast<const uint4*>(dy + (static_cast<long long>(row0) + i) * lddy + h * ATT_D + hh * 64);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 u = row_ok ? src2[g] : make_uint4(0, 0, 0, 0);
+        w[g * 4 + 0] = u.x; w[g * 4 + 1] = u.y; w[g * 4 + 2] = u.z; w[g * 4 + 3] = u.w;
+      }
+      tmem_st_32x32(lane_addr + TM_DO + hh * 32, w);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qdo_ready);
+    }
     int lo = 0, hi = T;
     float row_scale = p.scale;  // natural-log units here
     if (p.row_lo != nullptr && row_ok) {
@@ -213,7 +240,6 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
       if (kDrop && keep_row != nullptr && (j0 >> 5) < p.nw) kw = keep_row[j0 >> 5];
       mbar_wait(&sdp_full[bsel], (s >> 1) & 1);
       tc_fence_after();
-      if (s >= 2) mbar_wait(&buf_free[bsel], ((s >> 1) - 1) & 1);  // dS buffer consumed by dQ of sub-tile s-2
       uint32_t sv[32], dv[32];
       __syncwarp();
       tmem_ld_32x32(lane_addr + bsel * 128 + hh * 32, sv);
@@ -251,21 +277,19 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
 #pragma unroll
         for (int e = 0; e < 32; ++e) ds[e] *= __uint_as_float(dv[e]) - dlp;
       }
-      uint8_t* dsb = sDS + bsel * 16384;
+      // bf16 dS over the first 16 of the S columns this thread has just read (keys 32*hh.. of the sub-tile)
+      uint32_t pk[16];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const uint4 w = make_uint4(pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]), pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]),
-                                   pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]), pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]));
-        *reinterpret_cast<uint4*>(dsb + sw128_row64_off(r, hh * 32 + g * 8)) = w;
-      }
-      fence_proxy_async_smem();
+      for (int e = 0; e < 16; ++e) pk[e] = pack_bf16x2(ds[2 * e], ds[2 * e + 1]);
+      __syncwarp();
+      tmem_st_32x16(lane_addr + bsel * 128 + hh * 32, pk);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ds_full[bsel]);
     }
     // dQ epilogue: this thread stores columns [64*hh, 64*hh+64) of its row
-    const int last = n_sub - 1;
-    mbar_wait(&buf_free[last & 1], (last >> 1) & 1);
+    mbar_wait(dq_done, 0);
     tc_fence_after();
     __nv_bfloat16* drow = p.dq + (static_cast<long long>(row0) + i) * p.ldd + h * ATT_D;
     const float oscale = row_scale * inv_keep;
@@ -274,7 +298,7 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
       const int c = hh * 2 + cc;
       uint32_t o[32];
       __syncwarp();
-      tmem_ld_32x32(lane_addr + 256 + c * 32, o);
+      tmem_ld_32x32(lane_addr + TM_DQ + c * 32, o);
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
@@ -296,26 +320,26 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
 }
 
 // =============================================================================================
-// dK / dV kernel
+// dK / dV kernel (v6). Same finding as for dQ (operand fetch from shared memory bound the tensor pipe, and the
+// single P^T / dS^T smem tile serialised sub-tiles): P^T and dS^T are now written as bf16 INTO the score columns
+// their thread has just read and consumed from TMEM by dV += P^T dO and dK += dS^T Q. The per-query parameters are
+// staged per warp (each warp only needs the 32 queries of its column half), so the 8 compute warps no longer meet
+// at a block barrier every sub-tile (14 % of all stall samples in v5).
+//   TMEM  [0,128) / [128,256)  S^T (64 columns) | dP^T (64 columns), ping-pong;  [256,384) dV;  [384,512) dK
 // =============================================================================================
 constexpr uint32_t ATT_SUB_BYTES = 64 * 128 * 2;  // one [64 rows x 128] bf16 tile = two 8 KB swizzle sub-tiles
-// per 64-query sub-tile: 64 x float2 {-(max+lsum)*log2e, delta*(1-p)} + 64 x int2 {lo,hi} + 64 x float2 {max, lsum*log2e}
-// + 64 x float live + 4 x 64 keep words + 2 x int4 chunk ranges, rounded up
-constexpr uint32_t ATT_COL_STRIDE = 3072;
-constexpr int ATT_QDO_STAGES = 3;
+constexpr int ATT_QDO_STAGES = 4;
+// per warp and buffer: 32 x float2 {-(max+lsum)*log2e, delta*(1-p)} + 32 x int2 {lo,hi} + 32 x float2 {max, lsum*log2e}
+// + 32 x float live + 32 keep words
+constexpr uint32_t ATT_WPAR_BYTES = 1024;
 
 struct AttnDkvSmem {
   static constexpr uint32_t K_OFF = 0;
   static constexpr uint32_t V_OFF = K_OFF + ATT_TILE_BYTES;
-  // 3 TMA stages of 64 queries (16 KB each for Q and for dO): with 2 stages the ~1.5 us TMA round trip was exposed
-  // every other sub-tile (profiles/r01_attn_bwd_v4.details.txt: IPC 0.93, every pipe < 25 %)
   static constexpr uint32_t Q_OFF = V_OFF + ATT_TILE_BYTES;
   static constexpr uint32_t DO_OFF = Q_OFF + ATT_QDO_STAGES * ATT_SUB_BYTES;
-  static constexpr uint32_t PT_OFF = DO_OFF + ATT_QDO_STAGES * ATT_SUB_BYTES;  // [128 keys x 64 q] bf16, single buffer
-  static constexpr uint32_t DST_OFF = PT_OFF + 16384;
-  // per-query (column) parameters, double buffered (layout: see ATT_COL_STRIDE users in the kernel)
-  static constexpr uint32_t COL_OFF = DST_OFF + 16384;
-  static constexpr uint32_t BAR_OFF = COL_OFF + 2 * ATT_COL_STRIDE;
+  static constexpr uint32_t PAR_OFF = DO_OFF + ATT_QDO_STAGES * ATT_SUB_BYTES;  // [8 warps][2 buffers]
+  static constexpr uint32_t BAR_OFF = PAR_OFF + ATT_COMPUTE_WARPS * 2 * ATT_WPAR_BYTES;
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
 
@@ -329,18 +353,16 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint8_t* sV = smem + AttnDkvSmem::V_OFF;
   uint8_t* sQ = smem + AttnDkvSmem::Q_OFF;
   uint8_t* sDO = smem + AttnDkvSmem::DO_OFF;
-  uint8_t* sPT = smem + AttnDkvSmem::PT_OFF;
-  uint8_t* sDST = smem + AttnDkvSmem::DST_OFF;
-  uint8_t* sCol = smem + AttnDkvSmem::COL_OFF;
+  uint8_t* sPar = smem + AttnDkvSmem::PAR_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnDkvSmem::BAR_OFF);
   uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;   // [3]
-  uint64_t* qdo_free = bars + 4;   // [3] dV/dK MMAs that read Q/dO stage s completed
-  uint64_t* sdp_full = bars + 7;   // [2]
-  uint64_t* pds_full = bars + 9;   // [2]
-  uint64_t* grad_done = bars + 11; // dV/dK MMAs of a sub-tile completed: P^T / dS^T smem may be overwritten
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  unsigned int* s_rel = reinterpret_cast<unsigned int*>(bars + 13);  // relevance bits of the 64-query sub-tiles (<=128)
+  uint64_t* qdo_full = bars + 1;    // [4]
+  uint64_t* qdo_free = bars + 5;    // [4] dV/dK MMAs that read Q/dO stage s completed
+  uint64_t* sdp_full = bars + 9;    // [2]
+  uint64_t* pds_full = bars + 11;   // [2]
+  uint64_t* grads_done = bars + 13; // all dV/dK MMAs completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  unsigned int* s_rel = reinterpret_cast<unsigned int*>(bars + 15);  // relevance bits of the 64-query sub-tiles (<=128)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j0 = blockIdx.x * ATT_BN;
@@ -361,12 +383,21 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       mbar_init(&sdp_full[i], 1);
       mbar_init(&pds_full[i], ATT_COMPUTE_WARPS);
     }
-    mbar_init(grad_done, 1);
+    mbar_init(grads_done, 1);
     fence_barrier_init();
     s_rel[0] = s_rel[1] = s_rel[2] = s_rel[3] = 0;
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
   __syncthreads();
+  const int row0 = b * T;
+  const int qcol = h * ATT_D, kcol = C + h * ATT_D, vcol = 2 * C + h * ATT_D;
+  if (warp == 0 && lane == 0) {  // K / V do not depend on the relevance scan below: get them in flight first
+    mbar_expect_tx(kv_full, 2 * ATT_TILE_BYTES);
+    tma_load_2d(&tm_qkv, kv_full, sK, kcol, row0 + j0);
+    tma_load_2d(&tm_qkv, kv_full, sK + 16384, kcol + 64, row0 + j0);
+    tma_load_2d(&tm_qkv, kv_full, sV, vcol, row0 + j0);
+    tma_load_2d(&tm_qkv, kv_full, sV + 16384, vcol + 64, row0 + j0);
+  }
   // which 64-query sub-tiles can see this key tile at all
   if (p.row_lo != nullptr) {
     for (int i = threadIdx.x; i < T; i += blockDim.x) {
@@ -386,17 +417,10 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const unsigned int w = (it >> 5) == 0 ? rel0 : (it >> 5) == 1 ? rel1 : (it >> 5) == 2 ? rel2 : rel3;
     return (w >> (it & 31)) & 1u;
   };
-  const int row0 = b * T;
-  const int qcol = h * ATT_D, kcol = C + h * ATT_D, vcol = 2 * C + h * ATT_D;
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(kv_full, 2 * ATT_TILE_BYTES);
-      tma_load_2d(&tm_qkv, kv_full, sK, kcol, row0 + j0);
-      tma_load_2d(&tm_qkv, kv_full, sK + 16384, kcol + 64, row0 + j0);
-      tma_load_2d(&tm_qkv, kv_full, sV, vcol, row0 + j0);
-      tma_load_2d(&tm_qkv, kv_full, sV + 16384, vcol + 64, row0 + j0);
-      int n = 0, st = 0;
+      int st = 0;
       uint32_t ph = 0;
       for (int it = 0; it < nq; ++it) {
         if (!relevant(it)) continue;
@@ -407,7 +431,6 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         tma_load_2d(&tm_q64, &qdo_full[st], sQ + st * ATT_SUB_BYTES + 8192, qcol + 64, qrow);
         tma_load_2d(&tm_dy64, &qdo_full[st], sDO + st * ATT_SUB_BYTES, qcol, qrow);
         tma_load_2d(&tm_dy64, &qdo_full[st], sDO + st * ATT_SUB_BYTES + 8192, qcol + 64, qrow);
-        ++n;
         if (++st == ATT_QDO_STAGES) { st = 0; ph ^= 1; }
       }
     }
@@ -417,7 +440,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       int n_total = 0;
       for (int it = 0; it < nq; ++it) n_total += relevant(it) ? 1 : 0;
       mbar_wait(kv_full, 0);
-      auto issue_scores = [&](int n) {  // Q/dO stage n % 3, TMEM score buffer n & 1
+      auto issue_scores = [&](int n) {  // Q/dO stage n % 4, TMEM score buffer n & 1
         const int st = n % ATT_QDO_STAGES, tb = n & 1;
         mbar_wait(&qdo_full[st], (n / ATT_QDO_STAGES) & 1);
         tc_fence_after();
@@ -428,15 +451,17 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       };
       if (n_total > 0) issue_scores(0);
       for (int n = 0; n < n_total; ++n) {
+        // the scores of n+1 overwrite the buffer the gradient products of n-1 read from: MMAs execute in issue order
         if (n + 1 < n_total) issue_scores(n + 1);
         const int st = n % ATT_QDO_STAGES, tb = n & 1;
         mbar_wait(&pds_full[tb], (n >> 1) & 1);
         tc_fence_after();
-        issue_grad_128x128x64(tmem_base + 256, smem_u32(sPT), smem_u32(sDO + st * ATT_SUB_BYTES), 8192, n > 0);   // dV += P^T dO
-        issue_grad_128x128x64(tmem_base + 384, smem_u32(sDST), smem_u32(sQ + st * ATT_SUB_BYTES), 8192, n > 0);  // dK += dS^T Q
+        const uint32_t buf = tmem_base + tb * 128;
+        issue_grad_ts_128x128x64(tmem_base + 256, buf, buf + 32, smem_u32(sDO + st * ATT_SUB_BYTES), 8192, n > 0);      // dV += P^T dO
+        issue_grad_ts_128x128x64(tmem_base + 384, buf + 64, buf + 96, smem_u32(sQ + st * ATT_SUB_BYTES), 8192, n > 0);  // dK += dS^T Q
         umma_commit(&qdo_free[st]);
-        umma_commit(grad_done);
       }
+      umma_commit(grads_done);
     }
   } else {
     const int q = warp & 3;
@@ -444,65 +469,44 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const int r = q * 32 + lane;     // key row within the tile
     const int j = j0 + r;
     const bool key_ok = j < T;
+    const int kq0 = j0 + q * 32;     // first key of this warp
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const long long bh = static_cast<long long>(b) * p.H + h;
     const float inv_keep = kDrop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
     const float keep_frac = kDrop ? 1.0f - p.drop_p : 1.0f;
     const float sc2 = p.scale * LOG2E;
     const uint32_t mybit = 1u << keep_bit_pos(lane);  // this key's bit inside the keep word of its 32-key group
-    const int ct = threadIdx.x - 64;  // 0..255 among the compute threads
-    // Per-query parameters are software-pipelined: the global loads for the NEXT relevant sub-tile are issued before
-    // the math of the current one and written to the other smem buffer afterwards, so their latency never sits on
-    // the critical path.
+    uint8_t* wpar = sPar + (warp - 2) * 2 * ATT_WPAR_BYTES;
+    // Per-query parameters of THIS warp's 32 query columns (lane = query), software-pipelined: the global loads for
+    // the next relevant sub-tile are issued before the math of the current one and staged in the warp's other smem
+    // buffer afterwards; the math reads them back as warp-wide broadcasts.
     struct QParams { int lo, hi; float off, ls2, dl, live; uint32_t kw; };
     auto load_params = [&](int it) -> QParams {
       QParams z;
       z.lo = 0; z.hi = 0; z.off = 0.f; z.ls2 = 0.f; z.dl = 0.f; z.live = 1.f;  // query beyond T: contributes nothing
       z.kw = 0xffffffffu;
-      if (ct < 64) {
-        const int i = it * 64 + ct;
-        if (i < T) {
-          z.lo = 0; z.hi = T;
-          if (p.row_lo != nullptr) {
-            z.lo = p.row_lo[static_cast<long long>(b) * T + i];
-            z.hi = p.row_hi[static_cast<long long>(b) * T + i];
-            if (z.lo >= z.hi) { z.lo = 0; z.hi = T; z.live = 0.f; }  // fully-masked row: uniform P, no dS
-          }
-          z.off = p.lse[2 * (bh * T + i)];
-          z.ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
-          z.dl = p.delta[bh * T + i] * keep_frac;
+      const int i = it * 64 + hh * 32 + lane;
+      if (i < T) {
+        z.lo = 0; z.hi = T;
+        if (p.row_lo != nullptr) {
+          z.lo = p.row_lo[static_cast<long long>(b) * T + i];
+          z.hi = p.row_hi[static_cast<long long>(b) * T + i];
+          if (z.lo >= z.hi) { z.lo = 0; z.hi = T; z.live = 0.f; }  // fully-masked row: uniform P, no dS
         }
-      }
-      if (kDrop) {  // thread ct: query ct >> 2, key word ct & 3 of this 128-key tile
-        const int i = it * 64 + (ct >> 2);
-        const int w = (j0 >> 5) + (ct & 3);
-        if (i < T && w < p.nw) z.kw = p.keep[(bh * T + i) * p.nw + w];
+        z.off = p.lse[2 * (bh * T + i)];
+        z.ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
+        z.dl = p.delta[bh * T + i] * keep_frac;
+        if (kDrop && (kq0 >> 5) < p.nw) z.kw = p.keep[(bh * T + i) * p.nw + (kq0 >> 5)];
       }
       return z;
     };
     auto store_params = [&](int buf, const QParams& z) {
-      uint8_t* base = sCol + buf * ATT_COL_STRIDE;
-      float2* c_nd = reinterpret_cast<float2*>(base);          // {-(max + lsum) * log2e, delta * (1-p)}
-      int2* c_lh = reinterpret_cast<int2*>(base + 512);        // {lo, hi}
-      float2* c_x = reinterpret_cast<float2*>(base + 1024);    // {max (natural), lsum * log2e} (dense path)
-      float* c_live = reinterpret_cast<float*>(base + 1536);   // 0 for fully-masked queries
-      uint32_t* c_keep = reinterpret_cast<uint32_t*>(base + 1792);  // [4 key words][64 queries]
-      int4* c_rng = reinterpret_cast<int4*>(base + 2816);      // per 32-query chunk: {max lo, min hi}
-      if (ct < 64) {
-        c_nd[ct] = make_float2(-(z.off * LOG2E + z.ls2), z.dl);
-        c_lh[ct] = make_int2(z.lo, z.hi);
-        c_x[ct] = make_float2(z.off, z.ls2);
-        c_live[ct] = z.live;
-        // threads 0..63 are exactly two warps, one per 32-query chunk: interval common to the whole chunk
-        int mlo = (z.live == 0.f) ? 0x7fffffff : z.lo, mhi = z.hi;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          mlo = max(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
-          mhi = min(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
-        }
-        if ((ct & 31) == 0) c_rng[ct >> 5] = make_int4(mlo, mhi, 0, 0);
-      }
-      if (kDrop) c_keep[(ct & 3) * 64 + (ct >> 2)] = z.kw;
+      uint8_t* base = wpar + buf * ATT_WPAR_BYTES;
+      reinterpret_cast<float2*>(base)[lane] = make_float2(-(z.off * LOG2E + z.ls2), z.dl);
+      reinterpret_cast<int2*>(base + 256)[lane] = make_int2(z.lo, z.hi);
+      reinterpret_cast<float2*>(base + 512)[lane] = make_float2(z.off, z.ls2);
+      reinterpret_cast<float*>(base + 768)[lane] = z.live;
+      reinterpret_cast<uint32_t*>(base + 896)[lane] = z.kw;
     };
     auto next_relevant = [&](int it) -> int {
       ++it;
@@ -512,24 +516,27 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
     int n = 0;
     int it = next_relevant(-1);
+    QParams cur = {};
     if (it < nq) {
-      const QParams z0 = load_params(it);
-      store_params(0, z0);
+      cur = load_params(it);
+      store_params(0, cur);
     }
-    compute_bar_sync256();
+    __syncwarp();
     while (it < nq) {
       const int st = n & 1;
-      const int i0 = it * 64;
+      const int i0 = it * 64 + hh * 32;
       const int nx = next_relevant(it);
-      QParams zn;
+      QParams zn = {};
       if (nx < nq) zn = load_params(nx);  // in flight during the math below
-      const uint8_t* base = sCol + st * ATT_COL_STRIDE;
-      const float4* nd4 = reinterpret_cast<const float4*>(base) + hh * 16;               // two queries per float4
-      const int2* c_lh = reinterpret_cast<const int2*>(base + 512) + hh * 32;
-      const float2* c_x = reinterpret_cast<const float2*>(base + 1024) + hh * 32;
-      const float* c_live = reinterpret_cast<const float*>(base + 1536) + hh * 32;
-      const uint4* kp4 = reinterpret_cast<const uint4*>(base + 1792 + (q * 64 + hh * 32) * 4);  // four queries per uint4
-      const int4 rng = reinterpret_cast<const int4*>(base + 2816)[hh];
+      const uint8_t* base = wpar + st * ATT_WPAR_BYTES;
+      const float4* nd4 = reinterpret_cast<const float4*>(base);            // two queries per float4
+      const int2* c_lh = reinterpret_cast<const int2*>(base + 256);
+      const float2* c_x = reinterpret_cast<const float2*>(base + 512);
+      const float* c_live = reinterpret_cast<const float*>(base + 768);
+      const uint4* kp4 = reinterpret_cast<const uint4*>(base + 896);        // four queries per uint4
+      // every key of this warp visible to every (live) query of its 32 columns: one vote
+      const bool interior = (p.mask == nullptr) && (kq0 + 32 <= T) &&
+                            __all_sync(0xffffffffu, cur.live != 0.f && cur.lo <= kq0 && cur.hi >= kq0 + 32);
       mbar_wait(&sdp_full[st], (n >> 1) & 1);
       tc_fence_after();
       uint32_t sv[32], dv[32];
@@ -537,10 +544,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tmem_ld_32x32(lane_addr + st * 128 + hh * 32, sv);
       tmem_ld_32x32(lane_addr + st * 128 + 64 + hh * 32, dv);
       tmem_ld_wait();
-      float pt[32], dst[32];
-      // every key of this warp visible to every (live) query of the chunk: warp-uniform test
-      const bool interior = (p.mask == nullptr) && (j0 + q * 32 >= rng.x) && (j0 + q * 32 + 32 <= rng.y) &&
-                            (j0 + q * 32 + 32 <= T);
+      uint32_t ptw[16], dsw[16];  // bf16 pairs of P^T and dS^T
       if (interior) {
 #pragma unroll
         for (int e4 = 0; e4 < 8; ++e4) {
@@ -550,15 +554,13 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             const float4 nd = nd4[e4 * 2 + h2];
-            const float nneg[2] = {nd.x, nd.z}, dlp[2] = {nd.y, nd.w};
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int e = e4 * 4 + h2 * 2 + u;
-              const float pr = fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nneg[u]));
-              const bool kb = !kDrop || (kws[h2 * 2 + u] & mybit);
-              pt[e] = kb ? pr : 0.f;
-              dst[e] = pr * ((kb ? __uint_as_float(dv[e]) : 0.f) - dlp[u]);
-            }
+            const int e = e4 * 4 + h2 * 2;
+            const float pr0 = fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nd.x));
+            const float pr1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), sc2, nd.z));
+            const bool kb0 = !kDrop || (kws[h2 * 2] & mybit), kb1 = !kDrop || (kws[h2 * 2 + 1] & mybit);
+            ptw[e >> 1] = pack_bf16x2(kb0 ? pr0 : 0.f, kb1 ? pr1 : 0.f);
+            dsw[e >> 1] = pack_bf16x2(pr0 * ((kb0 ? __uint_as_float(dv[e]) : 0.f) - nd.y),
+                                      pr1 * ((kb1 ? __uint_as_float(dv[e + 1]) : 0.f) - nd.w));
           }
         }
       } else if (p.mask == nullptr) {
@@ -568,16 +570,22 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           if (kDrop) kk = kp4[e4];
           const uint32_t kws[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int e = e4 * 4 + u;
-            const float2 nd = reinterpret_cast<const float2*>(nd4)[e];
-            const int2 lh = c_lh[e];
-            const float live = c_live[e];
-            const bool vis = key_ok && j >= lh.x && j < lh.y;
-            const float pr = vis ? fast_exp2(fmaf(__uint_as_float(sv[e]) * live, sc2, nd.x)) : 0.f;
-            const bool kb = !kDrop || (kws[u] & mybit);
-            pt[e] = kb ? pr : 0.f;
-            dst[e] = pr * ((kb ? __uint_as_float(dv[e]) : 0.f) - nd.y) * live;
+          for (int h2 = 0; h2 < 2; ++h2) {
+            float prs[2], dss[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int e = e4 * 4 + h2 * 2 + u;
+              const float2 nd = reinterpret_cast<const float2*>(nd4)[e];
+              const int2 lh = c_lh[e];
+              const float live = c_live[e];
+              const bool vis = key_ok && j >= lh.x && j < lh.y;
+              const float pr = vis ? fast_exp2(fmaf(__uint_as_float(sv[e]) * live, sc2, nd.x)) : 0.f;
+              const bool kb = !kDrop || (kws[h2 * 2 + u] & mybit);
+              prs[u] = kb ? pr : 0.f;
+              dss[u] = pr * ((kb ? __uint_as_float(dv[e]) : 0.f) - nd.y) * live;
+            }
+            ptw[e4 * 2 + h2] = pack_bf16x2(prs[0], prs[1]);
+            dsw[e4 * 2 + h2] = pack_bf16x2(dss[0], dss[1]);
           }
         }
       } else {  // dense additive bias
@@ -587,44 +595,40 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           if (kDrop) kk = kp4[e4];
           const uint32_t kws[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int e = e4 * 4 + u;
-            const int i = i0 + hh * 32 + e;
-            const float2 nd = reinterpret_cast<const float2*>(nd4)[e];
-            const float2 cx = c_x[e];
-            const bool vis = key_ok && i < T;
-            const float bias =
-                vis ? __bfloat162float(p.mask[b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq + j]) : 0.f;
-            const float sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
-            const float pr = vis ? fast_exp2((sp - cx.x) * LOG2E - cx.y) : 0.f;
-            const bool kb = !kDrop || (kws[u] & mybit);
-            pt[e] = kb ? pr : 0.f;
-            dst[e] = pr * ((kb ? __uint_as_float(dv[e]) : 0.f) - nd.y);
+          for (int h2 = 0; h2 < 2; ++h2) {
+            float prs[2], dss[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int e = e4 * 4 + h2 * 2 + u;
+              const int i = i0 + e;
+              const float2 nd = reinterpret_cast<const float2*>(nd4)[e];
+              const float2 cx = c_x[e];
+              const bool vis = key_ok && i < T;
+              const float bias =
+                  vis ? __bfloat162float(p.mask[b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq + j]) : 0.f;
+              const float sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
+              const float pr = vis ? fast_exp2((sp - cx.x) * LOG2E - cx.y) : 0.f;
+              const bool kb = !kDrop || (kws[h2 * 2 + u] & mybit);
+              prs[u] = kb ? pr : 0.f;
+              dss[u] = pr * ((kb ? __uint_as_float(dv[e]) : 0.f) - nd.y);
+            }
+            ptw[e4 * 2 + h2] = pack_bf16x2(prs[0], prs[1]);
+            dsw[e4 * 2 + h2] = pack_bf16x2(dss[0], dss[1]);
           }
         }
       }
-      // the single P^T / dS^T smem tile is free once the dV/dK MMAs of the previous sub-tile have completed
-      if (n >= 1) mbar_wait(grad_done, (n - 1) & 1);
-      uint8_t* ptb = sPT;
-      uint8_t* dsb = sDST;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const uint32_t o = sw128_row64_off(r, hh * 32 + g * 8);
-        *reinterpret_cast<uint4*>(ptb + o) =
-            make_uint4(pack_bf16x2(pt[g * 8 + 0], pt[g * 8 + 1]), pack_bf16x2(pt[g * 8 + 2], pt[g * 8 + 3]),
-                       pack_bf16x2(pt[g * 8 + 4], pt[g * 8 + 5]), pack_bf16x2(pt[g * 8 + 6], pt[g * 8 + 7]));
-        *reinterpret_cast<uint4*>(dsb + o) =
-            make_uint4(pack_bf16x2(dst[g * 8 + 0], dst[g * 8 + 1]), pack_bf16x2(dst[g * 8 + 2], dst[g * 8 + 3]),
-                       pack_bf16x2(dst[g * 8 + 4], dst[g * 8 + 5]), pack_bf16x2(dst[g * 8 + 6], dst[g * 8 + 7]));
-      }
-      fence_proxy_async_smem();
+      // P^T over the first 16 of the S^T columns this thread has read, dS^T over the first 16 of its dP^T columns
+      __syncwarp();
+      tmem_st_32x16(lane_addr + st * 128 + hh * 32, ptw);
+      tmem_st_32x16(lane_addr + st * 128 + 64 + hh * 32, dsw);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full[st]);
-      // parameters of the next sub-tile into the other buffer (last read during sub-tile n-1, before the barrier
-      // that ended that iteration)
+      // parameters of the next sub-tile into the warp's other buffer (last read during sub-tile n-1)
       if (nx < nq) store_params(st ^ 1, zn);
-      compute_bar_sync256();
+      cur = zn;
+      __syncwarp();
       it = nx;
       ++n;
     }
@@ -633,7 +637,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     __nv_bfloat16* dkrow = p.dk + (static_cast<long long>(row0) + j) * p.ldd + h * ATT_D;
     const float oscale = hh == 0 ? inv_keep : inv_keep * p.scale;
     if (n > 0) {
-      mbar_wait(grad_done, (n - 1) & 1);
+      mbar_wait(grads_done, 0);
       tc_fence_after();
     }
 #pragma unroll 1
@@ -686,12 +690,11 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
   OBT_REQUIRE(drop_p == 0.f || keep != nullptr, "obt_attn_tc_bwd: dropout needs the keep mask (obt_attn_keep_mask)");
   const int C = H * d;
   const long long M = static_cast<long long>(B) * T;
-  CUtensorMap tm_qkv, tm_dy, tm_q64, tm_dy64;
+  OBT_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0,
+              "obt_attn_tc_bwd: qkv and dy must be 16-byte aligned");
+  CUtensorMap tm_qkv, tm_q64, tm_dy64;
   int rc = get_tensor_map_2d(&tm_qkv, qkv, static_cast<uint64_t>(3) * C, static_cast<uint64_t>(M),
                              static_cast<uint64_t>(ld), 64, 128);
-  if (rc) return rc;
-  rc = get_tensor_map_2d(&tm_dy, dy, static_cast<uint64_t>(C), static_cast<uint64_t>(M), static_cast<uint64_t>(lddy), 64,
-                         128);
   if (rc) return rc;
   rc = get_tensor_map_2d(&tm_q64, qkv, static_cast<uint64_t>(3) * C, static_cast<uint64_t>(M), static_cast<uint64_t>(ld),
                          64, 64);
@@ -736,9 +739,11 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
   }
   dim3 grid((T + ATT_BM - 1) / ATT_BM, H, B);
   if (drop_p > 0.f)
-    attn_tc_dq_kernel<true><<<grid, ATT_THREADS_BWD, AttnDqSmem::BYTES, stream>>>(tm_qkv, tm_dy, p, C);
+    attn_tc_dq_kernel<true><<<grid, ATT_THREADS_BWD, AttnDqSmem::BYTES, stream>>>(
+        tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
   else
-    attn_tc_dq_kernel<false><<<grid, ATT_THREADS_BWD, AttnDqSmem::BYTES, stream>>>(tm_qkv, tm_dy, p, C);
+    attn_tc_dq_kernel<false><<<grid, ATT_THREADS_BWD, AttnDqSmem::BYTES, stream>>>(
+        tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
   rc = check_launch("attn_tc_dq");
   if (rc) return rc;
   if (drop_p > 0.f)

@@ -101,6 +101,30 @@ __device__ __forceinline__ void issue_pv_ts_128x128x64(uint32_t d_tmem, uint32_t
   }
 }
 
+// D[128 x 64] = A * B^T with A = bf16 [128 x 128(d)] held in TMEM (64 columns, two d per column, lane = row) and
+// B = K-major [64 x 128(d)] smem tile (two 64-column sub-tiles `b_sub` bytes apart).
+__device__ __forceinline__ void issue_scores_ts_128x64(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, uint32_t b_sub) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, false);
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const uint64_t b_desc = make_smem_desc_sw128(b_addr + (kk >> 2) * b_sub + (kk & 3) * 32, 0, 1024);
+    umma_bf16_ts(d_tmem, a_tmem + kk * 8, b_desc, idesc, kk > 0 ? 1u : 0u);
+  }
+}
+
+// D[128 x 128(d)] += A[128 x 64] * B[64 x 128(d)] with A in TMEM as two 16-column pieces (reduction indices 0..31
+// at a_lo, 32..63 at a_hi: each compute thread wrote its piece over the score columns it had just read) and B read
+// MN-major from a TMA-written [64 rows x 128] tile whose two 64-column halves are `b_lbo` bytes apart.
+__device__ __forceinline__ void issue_grad_ts_128x128x64(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_addr,
+                                                         uint32_t b_lbo, bool accumulate) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, true);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const uint64_t b_desc = make_smem_desc_sw128(b_addr + kk * 2048, b_lbo, 1024);
+    umma_bf16_ts(d_tmem, (kk < 2 ? a_lo : a_hi) + (kk & 1) * 8, b_desc, idesc, (accumulate || kk > 0) ? 1u : 0u);
+  }
+}
+
 // byte offset of the 16-byte chunk [c, c+8) of row r in a [128 x 64] bf16 K-major tile (128-byte rows, 128B swizzle)
 __device__ __forceinline__ uint32_t sw128_row64_off(int r, int c) {
   return static_cast<uint32_t>(r * 128 + (((c >> 3) ^ (r & 7)) << 4));
