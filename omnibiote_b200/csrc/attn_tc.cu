@@ -98,7 +98,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // shuffled from lane 0 so that the compiler knows the value is warp-uniform: tcgen05 operands then go through
+  // uniform registers directly instead of a per-lane R2UR waterfall loop around every MMA
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tmem_slot), 0);
   int jb = 0, je = (T + FWD_BN - 1) / FWD_BN;
   if (p.row_lo != nullptr && s_range[2] == 0 && s_range[1] > s_range[0]) {
     jb = s_range[0] / FWD_BN;
@@ -131,34 +133,46 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t o_tmem = tmem_base + 128;
-      mbar_wait(q_full, 0);
-      const int pro = n_tiles < 2 ? n_tiles : 2;
-      for (int t = 0; t < pro; ++t) {  // S_0, S_1
-        mbar_wait(&k_full[t], 0);
-        tc_fence_after();
+    // The whole warp runs the (warp-uniform) control flow and waits; one elected lane issues. Keeping every operand
+    // provably uniform lets the compiler feed tcgen05.mma from uniform registers: with `if (lane == 0)` around the
+    // loop it wrapped EVERY MMA in a per-lane R2UR/ELECT waterfall loop (~13 instructions, profiles/r01_attn_v7).
+    const int n_t = __shfl_sync(0xffffffffu, n_tiles, 0);
+    const bool leader = elect_one();
+    const uint32_t q_addr = smem_u32(sQ);
+    const uint32_t o_tmem = tmem_base + 128;
+    mbar_wait(q_full, 0);
+    const int pro = n_t < 2 ? n_t : 2;
+    for (int t = 0; t < pro; ++t) {  // S_0, S_1
+      mbar_wait(&k_full[t], 0);
+      tc_fence_after();
+      if (leader) {
         issue_scores_128x64(tmem_base + t * 64, q_addr, 16384, smem_u32(sK + t * FWD_KV_BYTES), 8192);
         umma_commit(&s_full[t]);
         umma_commit(&k_empty[t]);
       }
-      for (int jj = 0; jj < n_tiles; ++jj) {
-        const int st = jj & 1;
-        const uint32_t par = (jj >> 1) & 1;
-        mbar_wait(&p_full[st], par);
-        mbar_wait(&v_full[st], par);
-        tc_fence_after();
+      __syncwarp();
+    }
+    for (int jj = 0; jj < n_t; ++jj) {
+      const int st = jj & 1;
+      const uint32_t par = (jj >> 1) & 1;
+      mbar_wait(&p_full[st], par);
+      mbar_wait(&v_full[st], par);
+      tc_fence_after();
+      if (leader) {
         issue_pv_ts_128x128x64(o_tmem, tmem_base + st * 64, smem_u32(sV + st * FWD_KV_BYTES), 8192, jj > 0);
         umma_commit(&v_empty[st]);
         umma_commit(pv_done);
-        if (jj + 2 < n_tiles) {  // S_{j+2} reuses the score buffer P_j was just read from (MMAs execute in order)
-          mbar_wait(&k_full[st], par ^ 1);
-          tc_fence_after();
+      }
+      __syncwarp();
+      if (jj + 2 < n_t) {  // S_{j+2} reuses the score buffer P_j was just read from (MMAs execute in order)
+        mbar_wait(&k_full[st], par ^ 1);
+        tc_fence_after();
+        if (leader) {
           issue_scores_128x64(tmem_base + st * 64, q_addr, 16384, smem_u32(sK + st * FWD_KV_BYTES), 8192);
           umma_commit(&s_full[st]);
           umma_commit(&k_empty[st]);
         }
+        __syncwarp();
       }
     }
   } else {

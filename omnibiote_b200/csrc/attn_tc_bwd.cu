@@ -117,7 +117,9 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // shuffled from lane 0 so that the compiler knows the value is warp-uniform: tcgen05 operands then go through
+  // uniform registers directly instead of a per-lane R2UR waterfall loop around every MMA
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tmem_slot), 0);
   int jb = 0, je = (T + ATT_BN - 1) / ATT_BN;
   if (p.row_lo != nullptr && s_range[2] == 0 && s_range[1] > s_range[0]) {
     jb = s_range[0] / ATT_BN;
@@ -146,37 +148,45 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(qdo_ready, 0);
-      // scores of sub-tile s: S -> buffer (s&1) columns [0,64), dP -> columns [64,128)
-      auto issue_scores = [&](int s) {
-        const int jj = s >> 1, hsub = s & 1, st = jj % ATT_DQ_KV_STAGES;
-        if (hsub == 0) {
-          const uint32_t ph = (jj / ATT_DQ_KV_STAGES) & 1;
-          mbar_wait(&k_full[st], ph);
-          mbar_wait(&v_full[st], ph);
-        }
-        tc_fence_after();
+    // The whole warp runs the warp-uniform control flow and waits; one elected lane issues (operands stay in
+    // uniform registers: no per-lane R2UR waterfall loop around every MMA).
+    const int n_sub_u = __shfl_sync(0xffffffffu, n_sub, 0);
+    const bool leader = elect_one();
+    mbar_wait(qdo_ready, 0);
+    // scores of sub-tile s: S -> buffer (s&1) columns [0,64), dP -> columns [64,128)
+    auto issue_scores = [&](int s) {
+      const int jj = s >> 1, hsub = s & 1, st = jj % ATT_DQ_KV_STAGES;
+      if (hsub == 0) {
+        const uint32_t ph = (jj / ATT_DQ_KV_STAGES) & 1;
+        mbar_wait(&k_full[st], ph);
+        mbar_wait(&v_full[st], ph);
+      }
+      tc_fence_after();
+      if (leader) {
         const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES) + hsub * 8192;
         const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES) + hsub * 8192;
         const uint32_t d = tmem_base + (s & 1) * 128;
         issue_scores_ts_128x64(d, tmem_base + TM_Q, k_addr, 16384);        // S  = Q K^T
         issue_scores_ts_128x64(d + 64, tmem_base + TM_DO, v_addr, 16384);  // dP = dO V^T
         umma_commit(&sdp_full[s & 1]);
-      };
-      issue_scores(0);
-      for (int s = 0; s < n_sub; ++s) {
-        // S(s+1) overwrites the buffer dQ(s-1) read its dS from: MMAs execute in issue order
-        if (s + 1 < n_sub) issue_scores(s + 1);
-        const int jj = s >> 1, hsub = s & 1, st = jj % ATT_DQ_KV_STAGES;
-        mbar_wait(&ds_full[s & 1], (s >> 1) & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+    };
+    issue_scores(0);
+    for (int s = 0; s < n_sub_u; ++s) {
+      // S(s+1) overwrites the buffer dQ(s-1) read its dS from: MMAs execute in issue order
+      if (s + 1 < n_sub_u) issue_scores(s + 1);
+      const int jj = s >> 1, hsub = s & 1, st = jj % ATT_DQ_KV_STAGES;
+      mbar_wait(&ds_full[s & 1], (s >> 1) & 1);
+      tc_fence_after();
+      if (leader) {
         const uint32_t k_rows = smem_u32(sK + st * ATT_TILE_BYTES) + hsub * 8192;  // key rows 64*hsub .. of the tile
         const uint32_t dsb = tmem_base + (s & 1) * 128;
         issue_grad_ts_128x128x64(tmem_base + TM_DQ, dsb, dsb + 32, k_rows, 16384, s > 0);  // dQ += dS K
         if (hsub == 1) umma_commit(&kv_empty[st]);
+        if (s == n_sub_u - 1) umma_commit(dq_done);
       }
-      umma_commit(dq_done);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
@@ -411,7 +421,9 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // shuffled from lane 0 so that the compiler knows the value is warp-uniform: tcgen05 operands then go through
+  // uniform registers directly instead of a per-lane R2UR waterfall loop around every MMA
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tmem_slot), 0);
   const unsigned int rel0 = s_rel[0], rel1 = s_rel[1], rel2 = s_rel[2], rel3 = s_rel[3];
   auto relevant = [&](int it) -> bool {
     const unsigned int w = (it >> 5) == 0 ? rel0 : (it >> 5) == 1 ? rel1 : (it >> 5) == 2 ? rel2 : rel3;
@@ -435,33 +447,40 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-      int n_total = 0;
-      for (int it = 0; it < nq; ++it) n_total += relevant(it) ? 1 : 0;
-      mbar_wait(kv_full, 0);
-      auto issue_scores = [&](int n) {  // Q/dO stage n % 4, TMEM score buffer n & 1
-        const int st = n % ATT_QDO_STAGES, tb = n & 1;
-        mbar_wait(&qdo_full[st], (n / ATT_QDO_STAGES) & 1);
-        tc_fence_after();
+    // whole warp in the uniform control flow, one elected issuer (see the dQ kernel)
+    const bool leader = elect_one();
+    const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+    int n_total = 0;
+    for (int it = 0; it < nq; ++it) n_total += relevant(it) ? 1 : 0;
+    n_total = __shfl_sync(0xffffffffu, n_total, 0);
+    mbar_wait(kv_full, 0);
+    auto issue_scores = [&](int n) {  // Q/dO stage n % 4, TMEM score buffer n & 1
+      const int st = n % ATT_QDO_STAGES, tb = n & 1;
+      mbar_wait(&qdo_full[st], (n / ATT_QDO_STAGES) & 1);
+      tc_fence_after();
+      if (leader) {
         const uint32_t d = tmem_base + tb * 128;
         issue_scores_128x64(d, k_addr, 16384, smem_u32(sQ + st * ATT_SUB_BYTES), 8192);        // S^T  = K Q^T
         issue_scores_128x64(d + 64, v_addr, 16384, smem_u32(sDO + st * ATT_SUB_BYTES), 8192);  // dP^T = V dO^T
         umma_commit(&sdp_full[tb]);
-      };
-      if (n_total > 0) issue_scores(0);
-      for (int n = 0; n < n_total; ++n) {
-        // the scores of n+1 overwrite the buffer the gradient products of n-1 read from: MMAs execute in issue order
-        if (n + 1 < n_total) issue_scores(n + 1);
-        const int st = n % ATT_QDO_STAGES, tb = n & 1;
-        mbar_wait(&pds_full[tb], (n >> 1) & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+    };
+    if (n_total > 0) issue_scores(0);
+    for (int n = 0; n < n_total; ++n) {
+      // the scores of n+1 overwrite the buffer the gradient products of n-1 read from: MMAs execute in issue order
+      if (n + 1 < n_total) issue_scores(n + 1);
+      const int st = n % ATT_QDO_STAGES, tb = n & 1;
+      mbar_wait(&pds_full[tb], (n >> 1) & 1);
+      tc_fence_after();
+      if (leader) {
         const uint32_t buf = tmem_base + tb * 128;
         issue_grad_ts_128x128x64(tmem_base + 256, buf, buf + 32, smem_u32(sDO + st * ATT_SUB_BYTES), 8192, n > 0);      // dV += P^T dO
         issue_grad_ts_128x128x64(tmem_base + 384, buf + 64, buf + 96, smem_u32(sQ + st * ATT_SUB_BYTES), 8192, n > 0);  // dK += dS^T Q
         umma_commit(&qdo_free[st]);
+        if (n == n_total - 1) umma_commit(grads_done);
       }
-      umma_commit(grads_done);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

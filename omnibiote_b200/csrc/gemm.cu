@@ -99,7 +99,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   if constexpr (kCluster == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // shuffled from lane 0 so that the compiler knows the value is warp-uniform (tcgen05 operands in uniform registers)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tmem_slot), 0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -176,12 +177,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && (kMode != 2 || cta_rank == 0)) {
+    // The whole warp runs the warp-uniform control flow and waits on the barriers; one elected lane issues. With
+    // `if (lane == 0)` around the loop the compiler wrapped every tcgen05.mma in a per-lane R2UR/ELECT waterfall loop
+    // (~13 instructions per MMA); with provably uniform operands the MMAs of a k-block issue back to back.
+    if (kMode != 2 || cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM_CTA * kCG, GEMM_BN, kAMN, kBMN);
       constexpr uint32_t A_LBO = kAMN ? GEMM_BK * 128 : 0;
       constexpr uint32_t B_LBO = kBMN ? GEMM_BK * 128 : 0;
       constexpr uint32_t A_KSTEP = kAMN ? 16 * 128 : 32;  // bytes per UMMA_K=16 step
       constexpr uint32_t B_KSTEP = kBMN ? 16 * 128 : 32;
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -197,23 +202,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+          if (leader) {
+            const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
+            const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            const uint64_t a_desc = make_smem_desc_sw128(a_addr + k * A_KSTEP, A_LBO, 1024);
-            const uint64_t b_desc = make_smem_desc_sw128(b_addr + k * B_KSTEP, B_LBO, 1024);
-            umma_bf16_ss<kCG>(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              const uint64_t a_desc = make_smem_desc_sw128(a_addr + k * A_KSTEP, A_LBO, 1024);
+              const uint64_t b_desc = make_smem_desc_sw128(b_addr + k * B_KSTEP, B_LBO, 1024);
+              umma_bf16_ss<kCG>(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            if constexpr (kMode == 1) umma_commit(&empty[stage]);
+            else if constexpr (kMode == 2) umma_commit_2sm(&empty[stage], 0x3);
+            else umma_commit_mc(&empty[stage], 0x3);
           }
-          if constexpr (kMode == 1) umma_commit(&empty[stage]);
-          else if constexpr (kMode == 2) umma_commit_2sm(&empty[stage], 0x3);
-          else umma_commit_mc(&empty[stage], 0x3);
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if constexpr (kCG == 1) umma_commit(&tfull[acc_stage]); else umma_commit_2sm(&tfull[acc_stage], 0x3);
+        if (leader) {
+          if constexpr (kCG == 1) umma_commit(&tfull[acc_stage]); else umma_commit_2sm(&tfull[acc_stage], 0x3);
+        }
+        __syncwarp();
       }
     }
   } else {

@@ -1,0 +1,19 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout -k 10 900 python -m pytest tests -q -m gpu -p no:cacheprovider --tb=short -x > gpurun_out/t20.log 2>&1
+echo "tests exit $?"; tail -n 6 gpurun_out/t20.log
+L=gpurun_out/probe20.log; : > $L
+run() { echo "--- $*" >> $L; timeout -k 5 120 python scripts/gemm_probe.py "$@" >> $L 2>&1; echo "exit $?" >> $L; }
+run 1 0 0 32768 4096 1024 t
+run 2 0 0 32768 4096 1024 t
+run 3 0 0 32768 4096 1024 t
+run 1 0 0 32768 1024 4096 t
+run 1 0 1 32768 1024 4096 t
+run 1 1 1 4096 1024 32768 t
+run 1 0 0 32768 3072 1024 t
+grep -E "^---|time|cuBLAS|bad=|exit [1-9]" $L
+timeout -k 10 600 python bench.py --steps 1 --warmup 3 --global-batch 128 --skip-cpu-baseline > gpurun_out/bench20.log 2>&1; echo "bench exit $?"; tail -n 1 gpurun_out/bench20.log | cut -c1-250
+timeout -k 10 600 python bench.py --steps 1 --warmup 3 --global-batch 32 --skip-cpu-baseline > gpurun_out/bench_plain.log 2>&1 &&
+timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches20.csv python bench.py --steps 1 --warmup 3 --global-batch 32 --skip-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+echo "ncu launches exit $?"
