@@ -244,12 +244,20 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             s[g * 8 + e] = (jbase + e < T) ? t : -INFINITY;
           }
         }
-      } else if (any_dead || !__all_sync(0xffffffffu, j0 >= lo && j0 + FWD_BN <= hi)) {
-        // tile straddles an interval end (or the end of the sequence) for some row of the warp
+      } else if (any_dead) {
 #pragma unroll
         for (int e = 0; e < 64; ++e) {
           const int j = j0 + e;
           s[e] = (j >= lo && j < hi) ? s[e] * live01 : -INFINITY;
+        }
+      } else if (!__all_sync(0xffffffffu, j0 >= lo && j0 + FWD_BN <= hi)) {
+        // tile straddles an interval end (or the end of the sequence) for some row of the warp: per-row visibility
+        // bits, one bit test per element
+        const uint32_t vm0 = interval_bits32(lo, hi, j0), vm1 = interval_bits32(lo, hi, j0 + 32);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          s[e] = (vm0 & (1u << e)) ? s[e] : -INFINITY;
+          s[32 + e] = (vm1 & (1u << e)) ? s[32 + e] : -INFINITY;
         }
       }
       // ---- row max of the tile, lazy update of the reference max

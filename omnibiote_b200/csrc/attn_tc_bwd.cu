@@ -256,6 +256,7 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
       tmem_ld_32x32(lane_addr + bsel * 128 + 64 + hh * 32, dv);
       tmem_ld_wait();
       float ds[32];  // first P, then dS
+      bool none_visible = false;
       if (p.mask != nullptr) {  // dense additive bias (kernel-uniform branch)
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
@@ -271,13 +272,21 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
 #pragma unroll
         for (int e = 0; e < 32; ++e) ds[e] = fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nneg));
       } else {
+        // the 32 keys straddle an interval end for some row: per-row visibility bits, one bit test per element
+        const uint32_t vm = row_ok ? interval_bits32(lo, hi, j0) : 0u;
+        if (__all_sync(0xffffffffu, vm == 0u)) {
+          none_visible = true;  // no row of the warp sees any of these keys: dS = 0, no exponentials
+        } else {
+          const float nneg = -neg;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int j = j0 + e;
-          ds[e] = (j >= lo && j < hi && row_ok) ? fast_exp2(__uint_as_float(sv[e]) * sc2 - neg) : 0.f;
+          for (int e = 0; e < 32; ++e)
+            ds[e] = (vm & (1u << e)) ? fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nneg)) : 0.f;
         }
       }
-      if (kDrop) {
+      if (none_visible) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) ds[e] = 0.f;
+      } else if (kDrop) {
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const float dpk = (kw & (1u << keep_bit_pos(e))) ? __uint_as_float(dv[e]) : 0.f;
@@ -340,8 +349,8 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
 constexpr uint32_t ATT_SUB_BYTES = 64 * 128 * 2;  // one [64 rows x 128] bf16 tile = two 8 KB swizzle sub-tiles
 constexpr int ATT_QDO_STAGES = 4;
 // per warp and buffer: 32 x float2 {-(max+lsum)*log2e, delta*(1-p)} + 32 x int2 {lo,hi} + 32 x float2 {max, lsum*log2e}
-// + 32 x float live + 32 keep words
-constexpr uint32_t ATT_WPAR_BYTES = 1024;
+// + 32 x float live + 32 keep words + 32 visibility words (which of the warp's 32 keys each query sees)
+constexpr uint32_t ATT_WPAR_BYTES = 1152;
 
 struct AttnDkvSmem {
   static constexpr uint32_t K_OFF = 0;
@@ -499,11 +508,12 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     // Per-query parameters of THIS warp's 32 query columns (lane = query), software-pipelined: the global loads for
     // the next relevant sub-tile are issued before the math of the current one and staged in the warp's other smem
     // buffer afterwards; the math reads them back as warp-wide broadcasts.
-    struct QParams { int lo, hi; float off, ls2, dl, live; uint32_t kw; };
+    struct QParams { int lo, hi; float off, ls2, dl, live; uint32_t kw, vm; };
     auto load_params = [&](int it) -> QParams {
       QParams z;
       z.lo = 0; z.hi = 0; z.off = 0.f; z.ls2 = 0.f; z.dl = 0.f; z.live = 1.f;  // query beyond T: contributes nothing
       z.kw = 0xffffffffu;
+      z.vm = 0u;
       const int i = it * 64 + hh * 32 + lane;
       if (i < T) {
         z.lo = 0; z.hi = T;
@@ -516,6 +526,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         z.ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
         z.dl = p.delta[bh * T + i] * keep_frac;
         if (kDrop && (kq0 >> 5) < p.nw) z.kw = p.keep[(bh * T + i) * p.nw + (kq0 >> 5)];
+        z.vm = interval_bits32(z.lo, z.hi, kq0);  // hi <= T: keys beyond the sequence are never visible
       }
       return z;
     };
@@ -526,6 +537,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       reinterpret_cast<float2*>(base + 512)[lane] = make_float2(z.off, z.ls2);
       reinterpret_cast<float*>(base + 768)[lane] = z.live;
       reinterpret_cast<uint32_t*>(base + 896)[lane] = z.kw;
+      reinterpret_cast<uint32_t*>(base + 1024)[lane] = z.vm;
     };
     auto next_relevant = [&](int it) -> int {
       ++it;
@@ -553,6 +565,8 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const float2* c_x = reinterpret_cast<const float2*>(base + 512);
       const float* c_live = reinterpret_cast<const float*>(base + 768);
       const uint4* kp4 = reinterpret_cast<const uint4*>(base + 896);        // four queries per uint4
+      const uint4* vp4 = reinterpret_cast<const uint4*>(base + 1024);
+      const uint32_t lanebit = 1u << lane;
       // every key of this warp visible to every (live) query of its 32 columns: one vote
       const bool interior = (p.mask == nullptr) && (kq0 + 32 <= T) &&
                             __all_sync(0xffffffffu, cur.live != 0.f && cur.lo <= kq0 && cur.hi >= kq0 + 32);
@@ -576,6 +590,31 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             const int e = e4 * 4 + h2 * 2;
             const float pr0 = fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nd.x));
             const float pr1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), sc2, nd.z));
+            const bool kb0 = !kDrop || (kws[h2 * 2] & mybit), kb1 = !kDrop || (kws[h2 * 2 + 1] & mybit);
+            ptw[e >> 1] = pack_bf16x2(kb0 ? pr0 : 0.f, kb1 ? pr1 : 0.f);
+            dsw[e >> 1] = pack_bf16x2(pr0 * ((kb0 ? __uint_as_float(dv[e]) : 0.f) - nd.y),
+                                      pr1 * ((kb1 ? __uint_as_float(dv[e + 1]) : 0.f) - nd.w));
+          }
+        }
+      } else if (p.mask == nullptr && __all_sync(0xffffffffu, cur.vm == 0u && cur.live != 0.f)) {
+        // no query of the chunk sees any key of this warp: P^T = dS^T = 0, no exponentials
+#pragma unroll
+        for (int e = 0; e < 16; ++e) ptw[e] = dsw[e] = 0u;
+      } else if (p.mask == nullptr && __all_sync(0xffffffffu, cur.live != 0.f)) {
+        // an interval end crosses the 32 x 32 block: per-query visibility words, one bit test per element
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {
+          uint4 kk = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+          if (kDrop) kk = kp4[e4];
+          const uint4 vv = vp4[e4];
+          const uint32_t kws[4] = {kk.x, kk.y, kk.z, kk.w};
+          const uint32_t vms[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const float4 nd = nd4[e4 * 2 + h2];
+            const int e = e4 * 4 + h2 * 2;
+            const float pr0 = (vms[h2 * 2] & lanebit) ? fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nd.x)) : 0.f;
+            const float pr1 = (vms[h2 * 2 + 1] & lanebit) ? fast_exp2(fmaf(__uint_as_float(sv[e + 1]), sc2, nd.z)) : 0.f;
             const bool kb0 = !kDrop || (kws[h2 * 2] & mybit), kb1 = !kDrop || (kws[h2 * 2 + 1] & mybit);
             ptw[e >> 1] = pack_bf16x2(kb0 ? pr0 : 0.f, kb1 ? pr1 : 0.f);
             dsw[e >> 1] = pack_bf16x2(pr0 * ((kb0 ? __uint_as_float(dv[e]) : 0.f) - nd.y),

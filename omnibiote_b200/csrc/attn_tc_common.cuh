@@ -130,6 +130,14 @@ __device__ __forceinline__ uint32_t sw128_row64_off(int r, int c) {
   return static_cast<uint32_t>(r * 128 + (((c >> 3) ^ (r & 7)) << 4));
 }
 
+// bit k set <=> position base + k lies in [lo, hi), k = 0..31
+__device__ __forceinline__ uint32_t interval_bits32(int lo, int hi, int base) {
+  const int a = min(max(lo - base, 0), 32), b = min(max(hi - base, 0), 32);
+  if (b <= a) return 0u;
+  const uint32_t upto_b = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
+  return upto_b & ~((1u << a) - 1u);  // a < 32 here
+}
+
 // named barrier among the 256 compute threads (warps 2..9)
 __device__ __forceinline__ void compute_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
