@@ -39,6 +39,9 @@ void obt_clear_descriptor_cache(void);
  *           2 aux_out = U = rb(acc); D = rb(gelu(U))   fused_gelu (model.py:23-25)
  *           3 D = rb(rb(acc) * gelu'(aux_in))          backward of fused_gelu, aux_in = U
  *           5 D = rb(aux_in + dropout(rb(acc)))        resid_dropout + residual (model.py:151,167,179-180)
+ *           7 D = rb(rotary(rb(acc))) on columns < rope_cols: apply_rotary_emb (model.py:39-50,108) fused into
+ *             c_attn; rope_cos / rope_sin are fp32 [rope_T, rope_head_dim/2] tables (position = row % rope_T),
+ *             rope_sin = NULL for the real bf16 freqs_cis buffer a bf16 model carries (cosine scaling)
  * gelu_mode: 0 = single rounding (TorchScript-fused execution), 1 = one bf16 rounding per primitive (eager CPU).
  * workspace (fp32, optional): enables split-K for small-output / long-reduction shapes (weight gradients).
  */
@@ -48,6 +51,7 @@ int obt_gemm_bf16(const void* A, const void* B, void* D, long long M, long long 
                   long long ldb, long long ldd, int a_mn_major, int b_mn_major, int epilogue, const void* aux_in,
                   long long ld_aux_in, void* aux_out, long long ld_aux_out, int gelu_mode, float drop_p,
                   unsigned long long seed, unsigned long long offset, void* workspace, long long workspace_elems,
+                  const float* rope_cos, const float* rope_sin, int rope_T, int rope_head_dim, int rope_cols,
                   cudaStream_t stream);
 
 /* ---- embedding: nn.Embedding + nn.Dropout(inplace) (model.py:241-242) ----------------------------------------- */
@@ -115,11 +119,14 @@ int obt_attn_tc_fwd(const void* qkv, long long ld, const void* mask, long long m
                     float scale, float drop_p, const unsigned int* keep, cudaStream_t stream);
 
 /* tensor-core backward (head_dim == 128): delta pre-pass + dQ kernel + dK/dV kernel. dqkv is the fused [M,3C]
- * gradient buffer (dq | dk | dv, pitch ldd); delta is fp32 [B,H,T] scratch; autograd adjoint of model.py:111-148. */
+ * gradient buffer (dq | dk | dv, pitch ldd); delta is fp32 [B,H,T] scratch; autograd adjoint of model.py:111-148.
+ * rope_cos / rope_sin (optional, fp32 [>=T, 64]): when given, the adjoint of apply_rotary_emb is applied to dq and dk
+ * in the kernels' epilogues (rope_sin = NULL: cosine scaling), so dqkv is the gradient of the PRE-rotary c_attn output. */
 int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, long long msb, long long msh, long long msq,
                     const int* row_lo, const int* row_hi, const void* y, long long ldy, const void* dy, long long lddy,
                     const float* lse, float* delta, void* dqkv, long long ldd, int B, int H, int T, int d, float scale,
-                    float drop_p, const unsigned int* keep, cudaStream_t stream);
+                    float drop_p, const unsigned int* keep, const float* rope_cos, const float* rope_sin,
+                    cudaStream_t stream);
 
 /* ---- attention-mask producers / compressors (input contract of the hot path) ------------------------------------
  * obt_doc_mask_intervals : per (b,i) visible key interval [lo,hi) from token ids = create_attention_mask

@@ -23,7 +23,7 @@ SIGNATURES = {
     "obt_gemm_set_cta_group": (None, [i32]),
     "obt_gemm_workspace_elems": (i64, [i64, i64, i64]),
     "obt_gemm_bf16": (i32, [vp, vp, vp, i64, i64, i64, i64, i64, i64, i32, i32, i32, vp, i64, vp, i64, i32, f32, u64,
-                            u64, vp, i64, vp]),
+                            u64, vp, i64, vp, vp, i32, i32, i32, vp]),
     "obt_embed_fwd": (i32, [vp, vp, vp, i64, i32, i32, f32, u64, u64, vp, vp]),
     "obt_embed_bwd": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, f32, u64, u64, vp]),
     "obt_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, f32, f32, vp]),
@@ -42,7 +42,7 @@ SIGNATURES = {
                                 i32, i32, i32, i32, f32, f32, vp, vp]),
     "obt_attn_tc_fwd": (i32, [vp, i64, vp, i64, i64, i64, vp, vp, vp, i64, vp, i32, i32, i32, i32, f32, f32, vp, vp]),
     "obt_attn_tc_bwd": (i32, [vp, i64, vp, i64, i64, i64, vp, vp, vp, i64, vp, i64, vp, vp, vp, i64, i32, i32, i32, i32,
-                              f32, f32, vp, vp]),
+                              f32, f32, vp, vp, vp, vp]),
     "obt_doc_mask_intervals": (i32, [vp, vp, vp, i32, i32, i64, i32, vp]),
     "obt_pad_mask_intervals": (i32, [vp, vp, vp, i32, i32, i64, vp]),
     "obt_mask_from_intervals": (i32, [vp, vp, vp, i32, i32, vp]),

@@ -320,13 +320,20 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
       tmem_ld_32x32(lane_addr + TM_DQ + c * 32, o);
       tmem_ld_wait();
       if (row_ok) {
+        float f[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(o[e]) * oscale;
+        if (p.rope_cos != nullptr) {  // adjoint of the rotary embedding: dqkv is the gradient of c_attn's raw output
+#pragma unroll
+          for (int e = 0; e < 32; ++e) f[e] = rb(f[e]);
+          const long long toff = static_cast<long long>(i) * (ATT_D / 2) + c * 16;
+          rope_adjoint32(f, p.rope_cos + toff, p.rope_sin ? p.rope_sin + toff : nullptr);
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          reinterpret_cast<uint4*>(drow + c * 32)[g] = make_uint4(
-              pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * oscale, __uint_as_float(o[g * 8 + 1]) * oscale),
-              pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * oscale, __uint_as_float(o[g * 8 + 3]) * oscale),
-              pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * oscale, __uint_as_float(o[g * 8 + 5]) * oscale),
-              pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * oscale, __uint_as_float(o[g * 8 + 7]) * oscale));
+          reinterpret_cast<uint4*>(drow + c * 32)[g] =
+              make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
+                         pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
       }
     }
     tc_fence_before();
@@ -712,13 +719,20 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       }
       if (key_ok) {
         __nv_bfloat16* dstp = (c < 4 ? dvrow : dkrow) + (c & 3) * 32;
+        float f[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(o[e]) * oscale;
+        if (c >= 4 && p.rope_cos != nullptr) {  // dK: adjoint of the rotary embedding at key position j
+#pragma unroll
+          for (int e = 0; e < 32; ++e) f[e] = rb(f[e]);
+          const long long toff = static_cast<long long>(j) * (ATT_D / 2) + (c & 3) * 16;
+          rope_adjoint32(f, p.rope_cos + toff, p.rope_sin ? p.rope_sin + toff : nullptr);
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          reinterpret_cast<uint4*>(dstp)[g] = make_uint4(
-              pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * oscale, __uint_as_float(o[g * 8 + 1]) * oscale),
-              pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * oscale, __uint_as_float(o[g * 8 + 3]) * oscale),
-              pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * oscale, __uint_as_float(o[g * 8 + 5]) * oscale),
-              pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * oscale, __uint_as_float(o[g * 8 + 7]) * oscale));
+          reinterpret_cast<uint4*>(dstp)[g] =
+              make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
+                         pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
       }
     }
     tc_fence_before();
@@ -738,8 +752,10 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
                                long long msq, const int* row_lo, const int* row_hi, const void* y, long long ldy,
                                const void* dy, long long lddy, const float* lse, float* delta, void* dqkv, long long ldd,
                                int B, int H, int T, int d, float scale, float drop_p, const unsigned int* keep,
-                               cudaStream_t stream) {
+                               const float* rope_cos, const float* rope_sin, cudaStream_t stream) {
   OBT_REQUIRE(qkv && y && dy && lse && delta && dqkv, "obt_attn_tc_bwd: null pointer");
+  OBT_REQUIRE((reinterpret_cast<uintptr_t>(rope_cos) & 15) == 0 && (reinterpret_cast<uintptr_t>(rope_sin) & 15) == 0,
+              "obt_attn_tc_bwd: rotary tables must be 16-byte aligned");
   OBT_REQUIRE(d == ATT_D, "obt_attn_tc_bwd: head_dim=%d, the tensor-core kernel is specialised for 128", d);
   OBT_REQUIRE(B > 0 && H > 0 && T > 0, "obt_attn_tc_bwd: empty problem");
   OBT_REQUIRE(T <= 128 * 64, "obt_attn_tc_bwd: T=%d exceeds %d", T, 128 * 64);
@@ -779,6 +795,8 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
   p.drop_p = drop_p;
   p.keep = keep;
   p.nw = keep_words(T);
+  p.rope_cos = rope_cos;
+  p.rope_sin = rope_cos ? rope_sin : nullptr;
   p.dq = static_cast<__nv_bfloat16*>(dqkv);
   p.dk = p.dq + C;
   p.dv = p.dq + 2 * C;

@@ -33,7 +33,35 @@ struct AttnTcParams {
   __nv_bfloat16* dk;
   __nv_bfloat16* dv;
   long long ldd;
+  // optional adjoint of the rotary embedding on dq / dk (fp32 tables [>= T, 64]; sin == nullptr: cosine scaling)
+  const float* rope_cos;
+  const float* rope_sin;
 };
+
+// adjoint rotary on 32 consecutive d-columns (16 pairs) of one gradient row, values already scaled (fp32)
+__device__ __forceinline__ void rope_adjoint32(float (&f)[32], const float* __restrict__ ct, const float* __restrict__ st) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 c4 = reinterpret_cast<const float4*>(ct)[g];
+    const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+    if (st != nullptr) {
+      const float4 s4 = reinterpret_cast<const float4*>(st)[g];
+      const float sn[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = f[g * 8 + 2 * j], b = f[g * 8 + 2 * j + 1];
+        f[g * 8 + 2 * j] = a * c[j] + b * sn[j];
+        f[g * 8 + 2 * j + 1] = b * c[j] - a * sn[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f[g * 8 + 2 * j] *= c[j];
+        f[g * 8 + 2 * j + 1] *= c[j];
+      }
+    }
+  }
+}
 
 // byte offset of the 16-byte chunk holding elements [c, c+8) of row r inside a [128 x 128] bf16 tile stored as two
 // [128 x 64] K-major sub-tiles with the 128B swizzle (what TMA SWIZZLE_128B produces and UMMA descriptors expect)

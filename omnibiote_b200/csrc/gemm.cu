@@ -359,12 +359,19 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
                              int epilogue, const void* aux_in, long long ld_aux_in, void* aux_out,
                              long long ld_aux_out, int gelu_mode, float drop_p, unsigned long long seed,
                              unsigned long long offset, void* workspace, long long workspace_elems,
-                             cudaStream_t stream) {
+                             const float* rope_cos, const float* rope_sin, int rope_T, int rope_head_dim,
+                             int rope_cols, cudaStream_t stream) {
   OBT_REQUIRE(A && B && D, "obt_gemm_bf16: null operand");
   OBT_REQUIRE(M > 0 && N > 0 && K > 0, "obt_gemm_bf16: empty problem M=%lld N=%lld K=%lld", M, N, K);
   OBT_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "obt_gemm_bf16: dims exceed int32");
-  OBT_REQUIRE(epilogue >= EPI_PLAIN && epilogue <= EPI_RESID_DROPOUT && epilogue != EPI_PARTIAL,
+  OBT_REQUIRE(((epilogue >= EPI_PLAIN && epilogue <= EPI_RESID_DROPOUT) || epilogue == EPI_ROPE) &&
+                  epilogue != EPI_PARTIAL,
               "obt_gemm_bf16: bad epilogue %d", epilogue);
+  if (epilogue == EPI_ROPE)
+    OBT_REQUIRE(rope_cos != nullptr && rope_T > 0 && rope_head_dim > 0 && rope_head_dim % 8 == 0 && rope_cols % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(rope_cos) & 15) == 0 && (reinterpret_cast<uintptr_t>(rope_sin) & 15) == 0,
+                "obt_gemm_bf16: rotary epilogue needs 16-byte aligned fp32 tables, head_dim %% 8 == 0 (got %d), "
+                "rope_cols %% 8 == 0 (got %d)", rope_head_dim, rope_cols);
   if (epilogue == EPI_RESID || epilogue == EPI_GELU_BWD || epilogue == EPI_RESID_DROPOUT)
     OBT_REQUIRE(aux_in != nullptr, "obt_gemm_bf16: epilogue %d needs aux_in", epilogue);
   if (epilogue == EPI_GELU) OBT_REQUIRE(aux_out != nullptr, "obt_gemm_bf16: GELU epilogue needs aux_out");
@@ -373,7 +380,13 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   // auto: one CTA per SM with 128x256 tiles measured 1.17-1.40 PFLOP/s on the block/head shapes (86-95 % of cuBLAS);
   // the CTA-pair variant stays selectable for ablations (obt_gemm_set_cta_group).
   // mode 3 = cluster of two such CTAs sharing (multicasting) the B tile.
-  if (cg == 0) cg = g_auto_mode;
+  if (cg == 0) {
+    // measured on the block / head shapes (profiles/r01_gemm_modes_v2.txt): sharing the B tile between two CTAs by
+    // TMA multicast wins 2-6 % when the reduction is short (K <= 3072: more tile switches per byte) and on the
+    // split-K weight-gradient shapes; the plain one-CTA kernel wins 2-8 % on the long reductions.
+    const bool small_wgrad = a_mn_major && b_mn_major && M * N <= 8ll * 1024 * 1024;
+    cg = (K <= 3072 || small_wgrad) ? 3 : g_auto_mode;
+  }
   if (cg == 3 && M <= GEMM_BM_CTA) cg = 1;  // a single row block has no partner to share B with
   const int cluster = (cg == 1) ? 1 : 2;     // 128-row blocks per tile / CTAs per cluster
   const int bm = GEMM_BM_CTA * cluster;
@@ -396,6 +409,11 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   p.drop_p = drop_p;
   p.seed = seed;
   p.offset = offset;
+  p.rope_cos = rope_cos;
+  p.rope_sin = rope_sin;
+  p.rope_T = rope_T;
+  p.rope_d = rope_head_dim;
+  p.rope_cols = rope_cols;
   auto aligned16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
   p.vec_ok = (N % 8 == 0) && (ldd % 8 == 0) && aligned16(D) &&
              (aux_in == nullptr || (ld_aux_in % 8 == 0 && aligned16(aux_in))) &&

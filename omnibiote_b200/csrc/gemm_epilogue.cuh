@@ -23,6 +23,8 @@ enum : int {
   EPI_PARTIAL = 4,   // split-K: fp32 partial tile -> workspace[split]
   EPI_RESID_DROPOUT = 5,  // D = rb(float(aux_in) + float(rb(rb(acc) * keep/(1-p))))   (resid_dropout, model.py:151,167)
   EPI_GELU_EAGER = 6,     // internal: EPI_GELU with one bf16 rounding per primitive (gelu_mode = 1)
+  EPI_ROPE = 7,           // D = rb(rotary(rb(acc))) on columns < rope_cols (q | k of the fused c_attn output):
+                          // apply_rotary_emb (model.py:39-50,108) fused into the c_attn GEMM
 };
 
 struct GemmParams {
@@ -38,6 +40,10 @@ struct GemmParams {
   float* partial;
   float drop_p;
   unsigned long long seed, offset;
+  // EPI_ROPE: fp32 tables [rope_T rows, rope_d / 2]; rope_sin == nullptr -> cosine scaling (real bf16 freqs_cis)
+  const float* rope_cos;
+  const float* rope_sin;
+  int rope_T, rope_d, rope_cols;
 };
 
 constexpr int GEMM_BK = 64;
@@ -93,6 +99,25 @@ __device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
 }
 __device__ __forceinline__ uint4 pack8f(const float (&f)[8]) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// rotary of 4 adjacent (even, odd) pairs: cs/sn are the table entries of the pairs; sn == nullptr semantics are
+// expressed by has_sin = false (cosine scaling). inverse = adjoint rotation (backward).
+__device__ __forceinline__ void rope8(float (&v)[8], const float4& cs, const float4& sn, bool has_sin, bool inverse) {
+  const float c[4] = {cs.x, cs.y, cs.z, cs.w};
+  const float s4[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (has_sin) {
+      const float sj = inverse ? -s4[j] : s4[j];
+      const float a = v[2 * j], b = v[2 * j + 1];
+      v[2 * j] = a * c[j] - b * sj;
+      v[2 * j + 1] = a * sj + b * c[j];
+    } else {
+      v[2 * j] *= c[j];
+      v[2 * j + 1] *= c[j];
+    }
+  }
 }
 
 template <int EPI>
@@ -204,6 +229,15 @@ __device__ __noinline__ void epilogue_segment_slow(const GemmParams& p, uint4 w,
     if constexpr (EpiTraits<EPI>::kAuxIn)
       if (e < nvalid) a[e] = __bfloat162float(p.aux_in[grow * p.ld_aux_in + gcol + e]);
   }
+  if constexpr (EPI == EPI_ROPE) {  // rope_cols, rope_d are multiples of 8: a chunk is either all rotary or none
+    if (gcol < p.rope_cols) {
+      const long long off = (grow % p.rope_T) * (p.rope_d >> 1) + ((gcol % p.rope_d) >> 1);
+      const float4 cs = *reinterpret_cast<const float4*>(p.rope_cos + off);
+      float4 sn = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.rope_sin != nullptr) sn = *reinterpret_cast<const float4*>(p.rope_sin + off);
+      rope8(v, cs, sn, p.rope_sin != nullptr, false);
+    }
+  }
   epilogue_math<EPI>(p, v, a, u, grow, gcol);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -247,11 +281,22 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {
         uint4 w[4], ax[4];
+        float4 rc[4], rs[4];
         // staged values and aux loads of the group first (independent loads in flight together) ...
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int rl = (hf * 4 + it) * 4 + rsub;
           w[it] = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((seg ^ (rl & 7)) << 4));
+          if constexpr (EPI == EPI_ROPE) {
+            const long long grow = row_base + rl;
+            rc[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+            rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grow < p.M && gcol < p.rope_cols) {
+              const long long off = (grow % p.rope_T) * (p.rope_d >> 1) + ((gcol % p.rope_d) >> 1);
+              rc[it] = *reinterpret_cast<const float4*>(p.rope_cos + off);
+              if (p.rope_sin != nullptr) rs[it] = *reinterpret_cast<const float4*>(p.rope_sin + off);
+            }
+          }
           if constexpr (EpiTraits<EPI>::kAuxIn) {
             const long long grow = row_base + rl;
             ax[it] = make_uint4(0, 0, 0, 0);
@@ -268,6 +313,9 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
               float v[8], a[8], u[8];
               unpack8f(w[it], v);
               if constexpr (EpiTraits<EPI>::kAuxIn) unpack8f(ax[it], a);
+              if constexpr (EPI == EPI_ROPE) {
+                if (gcol < p.rope_cols) rope8(v, rc[it], rs[it], p.rope_sin != nullptr, false);
+              }
               epilogue_math<EPI>(p, v, a, u, grow, gcol);
               if constexpr (EpiTraits<EPI>::kAuxOut)
                 *reinterpret_cast<uint4*>(p.aux_out + grow * p.ld_aux_out + gcol) = pack8f(u);
@@ -296,6 +344,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const GemmParams& p, uint32_t
     case EPI_RESID_DROPOUT:
       epilogue_chunks<EPI_RESID_DROPOUT>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end);
       break;
+    case EPI_ROPE: epilogue_chunks<EPI_ROPE>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
     default: epilogue_chunks<EPI_GELU_EAGER>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
   }
 }

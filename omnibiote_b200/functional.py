@@ -105,8 +105,8 @@ class BlockFunction(torch.autograd.Function):
         scale = 8.0 / C  # model.py:119,135: 8 / n_embd, independent of n_head
 
         h1, _, mean1, rstd1 = ops.layernorm_fwd(x, g1)
-        qkv = ops.gemm(h1, w_qkv)
-        ops.rope_(qkv, cos_tab, sin_tab, T, C, d)
+        # c_attn with the rotary embedding of q and k fused into the GEMM epilogue (model.py:102-108)
+        qkv = ops.gemm(h1, w_qkv, epilogue=ops.EPI_ROPE, rope=(cos_tab, sin_tab, T, d, 2 * C))
         keep = ops.attn_keep_mask(B, H, T, p, *seeds[0], dev) if p > 0.0 else None
         y, lse = ops.attention_fwd(qkv, B, T, H, d, scale, mask, p, keep)
         if p > 0.0:
@@ -153,8 +153,8 @@ class BlockFunction(torch.autograd.Function):
         d_a = ops.dropout(dx1, p, *seeds[1]) if p > 0.0 else dx1
         dw_o = _wgrad(d_a, y, po)
         dy = ops.gemm(d_a, w_o, b_mn=True)
-        dqkv = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, ctx.mask, p, ctx.keep)
-        ops.rope_(dqkv, cos_tab, sin_tab, T, C, d, inverse=True)
+        # rotary adjoint fused into the dQ / dK epilogues: dqkv is the gradient of c_attn's raw output
+        dqkv = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, ctx.mask, p, ctx.keep, rope=(cos_tab, sin_tab))
         dw_qkv = _wgrad(dqkv, h1, pqkv)
         dh1 = ops.gemm(dqkv, w_qkv, b_mn=True)
         acc1 = direct and pg1.grad is not None

@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 
-EPI_PLAIN, EPI_RESID, EPI_GELU, EPI_GELU_BWD, EPI_RESID_DROPOUT = 0, 1, 2, 3, 5
+EPI_PLAIN, EPI_RESID, EPI_GELU, EPI_GELU_BWD, EPI_RESID_DROPOUT, EPI_ROPE = 0, 1, 2, 3, 5, 7
 
 # gelu_mode 0: one rounding (TorchScript-fused execution on CUDA); 1: a bf16 rounding per primitive (eager CPU run of
 # the same expression, which is what the CPU oracle does). See SURVEY Appendix A.2.
@@ -76,8 +76,10 @@ def _mat(t: torch.Tensor, name: str):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a_mn: bool = False, b_mn: bool = False,
          epilogue: int = EPI_PLAIN, aux_in: torch.Tensor | None = None, aux_out: torch.Tensor | None = None,
-         drop_p: float = 0.0, seed: int = 0, offset: int = 0, allow_splitk: bool = True) -> torch.Tensor:
-    """out[M,N] = epilogue(op(a) @ op(b)^T).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn)."""
+         drop_p: float = 0.0, seed: int = 0, offset: int = 0, allow_splitk: bool = True,
+         rope: tuple | None = None) -> torch.Tensor:
+    """out[M,N] = epilogue(op(a) @ op(b)^T).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn).
+    rope = (cos_tab, sin_tab | None, T, head_dim, n_cols) with epilogue=EPI_ROPE: rotary on the first n_cols columns."""
     a, lda = _mat(a, "gemm A")
     b, ldb = _mat(b, "gemm B")
     M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
@@ -98,6 +100,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a
     if allow_splitk and K >= 1024 and M * N <= 8 * 1024 * 1024:
         ws_elems = 8 * M * N
         ws = workspace("splitk", ws_elems, torch.float32, a.device)
+    rope_cos = rope_sin = None
+    rope_T = rope_d = rope_cols = 0
+    if epilogue == EPI_ROPE:
+        if rope is None:
+            raise RuntimeError("omnibiote_b200: EPI_ROPE needs rope=(cos, sin, T, head_dim, n_cols)")
+        rope_cos, rope_sin, rope_T, rope_d, rope_cols = rope
+        _req(rope_cos, "cos table", torch.float32)
+        if rope_cos.shape[0] < rope_T:
+            raise RuntimeError("omnibiote_b200: rotary table shorter than the sequence")
     lib = _lib.load()
     prof = PROFILE_GEMM
     if prof is not None:
@@ -105,7 +116,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a
         ev0.record()
     rc = lib.obt_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldd, int(a_mn), int(b_mn),
                            epilogue, _ptr(aux_in), ld_ai, _ptr(aux_out), ld_ao, GELU_MODE, float(drop_p), seed, offset,
-                           _ptr(ws), ws_elems, _stream())
+                           _ptr(ws), ws_elems, _ptr(rope_cos), _ptr(rope_sin), int(rope_T), int(rope_d), int(rope_cols),
+                           _stream())
     _lib.check(rc, "obt_gemm_bf16")
     if prof is not None:
         ev1.record()
@@ -310,8 +322,11 @@ def attention_fwd(qkv: torch.Tensor, B: int, T: int, H: int, d: int, scale: floa
     return y, lse
 
 
-def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, keep=None, impl: str = "auto"):
-    """Returns dqkv [M,3C] (gradient w.r.t. the post-rotary q,k and v). keep: the forward's keep mask."""
+def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, keep=None, impl: str = "auto",
+                  rope: tuple | None = None):
+    """Returns dqkv [M,3C]: the gradient w.r.t. the post-rotary q,k and v, or, with rope=(cos_tab, sin_tab | None),
+    w.r.t. the PRE-rotary c_attn output (the rotary adjoint is applied in the kernels' epilogues).
+    keep: the forward's keep mask."""
     if drop_p > 0.0 and keep is None:
         raise RuntimeError("omnibiote_b200: attention dropout needs the keep mask (ops.attn_keep_mask)")
     qkv, ld = _mat(qkv, "qkv")
@@ -333,7 +348,7 @@ def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, ke
                                          _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0,
                                          y.data_ptr(), C, dy.data_ptr(), lddy, lse.data_ptr(), delta.data_ptr(),
                                          dqkv.data_ptr(), 3 * C, B, H, T, d, scale, float(drop_p), _ptr(keep),
-                                         _stream())
+                                         _ptr(rope[0]) if rope else 0, _ptr(rope[1]) if rope else 0, _stream())
         _lib.check(rc, "obt_attn_tc_bwd")
         return dqkv
     rc = _lib.load().obt_attn_simt_bwd(q, k, v, ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
@@ -341,6 +356,8 @@ def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, ke
                                        y.data_ptr(), C, dy.data_ptr(), lddy, lse.data_ptr(), delta.data_ptr(), dq, dk,
                                        dv, 3 * C, B, H, T, d, scale, float(drop_p), _ptr(keep), _stream())
     _lib.check(rc, "obt_attn_simt_bwd")
+    if rope is not None:
+        rope_(dqkv, rope[0], rope[1], T, C, d, inverse=True)
     return dqkv
 
 

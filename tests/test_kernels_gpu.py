@@ -83,6 +83,40 @@ def test_rope_real_table_is_cosine_scaling_and_complex_is_rotation():
     assert rel_err(back[:, :2 * C], qkv[:, :2 * C]) < 8e-3
 
 
+@pytest.mark.parametrize("complex_table", [False, True])
+def test_rope_fused_into_gemm_epilogue_and_attention_backward(complex_table):
+    """The fused paths (c_attn GEMM epilogue; dQ / dK epilogues of the attention backward) against the stand-alone
+    rotary kernel applied to the un-fused results."""
+    ops = _ops()
+    B, T, H, d = 2, 256, 2, 128
+    C = H * d
+    ang = torch.outer(torch.arange(T, device="cuda").float(),
+                      1.0 / (10000 ** (torch.arange(0, d, 2, device="cuda").float() / d)))
+    if complex_table:
+        cos, sin = torch.cos(ang).contiguous(), torch.sin(ang).contiguous()
+    else:
+        cos, sin = torch.cos(ang).to(BF).float().contiguous(), None
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = (torch.randn(B * T, C, generator=g, device="cuda") * 0.5).to(BF)
+    w = (torch.randn(3 * C, C, generator=g, device="cuda") * 0.05).to(BF)
+    plain = ops.gemm(x, w)
+    want = ops.rope_(plain.clone(), cos, sin, T, C, d)
+    fused = ops.gemm(x, w, epilogue=ops.EPI_ROPE, rope=(cos, sin, T, d, 2 * C))
+    same = (lambda a, b: rel_err(a, b) < 1e-3) if complex_table else torch.equal  # fma contraction may differ
+    assert same(fused, want)                   # same roundings: rb(acc), then rotary in fp32, then rb
+    # backward: rotary adjoint inside the dQ / dK epilogues
+    qkv = want
+    spec = ops.MaskSpec(None, B, H, T)
+    y, lse = ops.attention_fwd(qkv, B, T, H, d, 8.0 / C, spec, 0.0, None, impl="tc")
+    dy = torch.randn(B * T, C, generator=g, device="cuda").to(BF)
+    g0 = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, 8.0 / C, spec, 0.0, None, impl="tc")
+    want_g = ops.rope_(g0.clone(), cos, sin, T, C, d, inverse=True)
+    g1 = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, 8.0 / C, spec, 0.0, None, impl="tc", rope=(cos, sin))
+    assert same(g1, want_g)
+    g2 = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, 8.0 / C, spec, 0.0, None, impl="simt", rope=(cos, sin))
+    assert rel_err(g2, want_g) < 1.5e-2
+
+
 def _sdpa_ref(qkv, B, T, H, d, scale, mask4):
     C = H * d
     q, k, v = [t.view(B, T, H, d).transpose(1, 2).float() for t in qkv.float().split(C, dim=1)]
