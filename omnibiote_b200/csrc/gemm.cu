@@ -84,7 +84,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], kCG);
+      // mode 2: ONE arrival (the leader's expect_tx covering the bytes of both CTAs); the peer's TMA loads signal
+      // the leader's barrier through their transaction bytes alone (an explicit remote arrive per k-block needed a
+      // release fence = MEMBAR + ERRBAR in the peer's producer and halved the kernel's throughput)
+      mbar_init(&full[i], 1);
       mbar_init(&empty[i], kMode == 3 ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -166,7 +169,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int j = 0; j < Cfg::BNL / 64; ++j)
                 tma_load_2d_2sm(&tmB, &full[stage], b_dst + j * 8192, n0 + j * 64, k0);
             }
-            if (cta_rank != 0) mbar_arrive_cluster(&full[stage], 0);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -250,7 +252,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (kCG == 1) mbar_arrive(&tempty[acc_stage]); else mbar_arrive_cluster(&tempty[acc_stage], 0);
+        // (TMEM reads are ordered by the tcgen05 fences; the remote arrive itself needs no release fence)
+        if constexpr (kCG == 1) mbar_arrive(&tempty[acc_stage]); else mbar_arrive_cluster_relaxed(&tempty[acc_stage], 0);
       }
     }
   }
@@ -339,7 +342,6 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 }
 
 static int g_force_cta_group = 0;  // 0 = auto, 1 / 2 / 3 = forced kernel mode (tests / ablations)
-static int g_auto_mode = 1;        // what "auto" resolves to
 
 }  // namespace obt
 
@@ -380,13 +382,11 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   // auto: one CTA per SM with 128x256 tiles measured 1.17-1.40 PFLOP/s on the block/head shapes (86-95 % of cuBLAS);
   // the CTA-pair variant stays selectable for ablations (obt_gemm_set_cta_group).
   // mode 3 = cluster of two such CTAs sharing (multicasting) the B tile.
-  if (cg == 0) {
-    // measured on the block / head shapes (profiles/r01_gemm_modes_v2.txt): sharing the B tile between two CTAs by
-    // TMA multicast wins 2-6 % when the reduction is short (K <= 3072: more tile switches per byte) and on the
-    // split-K weight-gradient shapes; the plain one-CTA kernel wins 2-8 % on the long reductions.
-    const bool small_wgrad = a_mn_major && b_mn_major && M * N <= 8ll * 1024 * 1024;
-    cg = (K <= 3072 || small_wgrad) ? 3 : g_auto_mode;
-  }
+  // auto: CTA pairs (cta_group::2, 256 x 256 tiles, each CTA holding half of B) measured 1.29-1.47 PFLOP/s on every
+  // block / head shape (profiles/r01_gemm_modes_v3.txt), level with cuBLAS and 3-15 % above the one-CTA (mode 1) and
+  // multicast-cluster (mode 3) kernels, which stay selectable for ablations (obt_gemm_set_cta_group).
+  if (cg == 0) cg = 2;
+  if (cg == 2 && M <= GEMM_BM_CTA) cg = 1;  // a single 128-row block has no partner
   if (cg == 3 && M <= GEMM_BM_CTA) cg = 1;  // a single row block has no partner to share B with
   const int cluster = (cg == 1) ? 1 : 2;     // 128-row blocks per tile / CTAs per cluster
   const int bm = GEMM_BM_CTA * cluster;
