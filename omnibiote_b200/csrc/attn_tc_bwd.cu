@@ -426,10 +426,24 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
   // which 64-query sub-tiles can see this key tile at all
   if (p.row_lo != nullptr) {
-    for (int i = threadIdx.x; i < T; i += blockDim.x) {
-      const int lo = p.row_lo[static_cast<long long>(b) * T + i], hi = p.row_hi[static_cast<long long>(b) * T + i];
-      const bool rel = (lo >= hi) || (lo < j0 + ATT_BN && hi > j0);
-      if (rel) atomicOr(&s_rel[(i >> 6) >> 5], 1u << ((i >> 6) & 31));
+    // four rows per thread and pass: all loads in flight before the first dependent atomic
+    for (int i0 = threadIdx.x; i0 < T; i0 += 4 * blockDim.x) {
+      int lo[4], hi[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        lo[u] = 1; hi[u] = 1;  // beyond T: an empty, irrelevant interval
+        if (i < T) {
+          lo[u] = p.row_lo[static_cast<long long>(b) * T + i];
+          hi[u] = p.row_hi[static_cast<long long>(b) * T + i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        const bool rel = i < T && ((lo[u] >= hi[u]) || (lo[u] < j0 + ATT_BN && hi[u] > j0));
+        if (rel) atomicOr(&s_rel[(i >> 6) >> 5], 1u << ((i >> 6) & 31));
+      }
     }
   } else if (threadIdx.x < 4) {
     s_rel[threadIdx.x] = 0xffffffffu;
@@ -515,6 +529,8 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     // Per-query parameters of THIS warp's 32 query columns (lane = query), software-pipelined: the global loads for
     // the next relevant sub-tile are issued before the math of the current one and staged in the warp's other smem
     // buffer afterwards; the math reads them back as warp-wide broadcasts.
+    // load_params only ISSUES the global loads (raw values; no arithmetic or branches on loaded data, which would
+    // stall the in-order warp right there); finish_params turns them into the staged form after the math.
     struct QParams { int lo, hi; float off, ls2, dl, live; uint32_t kw, vm; };
     auto load_params = [&](int it) -> QParams {
       QParams z;
@@ -523,19 +539,27 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       z.vm = 0u;
       const int i = it * 64 + hh * 32 + lane;
       if (i < T) {
-        z.lo = 0; z.hi = T;
+        z.hi = T;
         if (p.row_lo != nullptr) {
           z.lo = p.row_lo[static_cast<long long>(b) * T + i];
           z.hi = p.row_hi[static_cast<long long>(b) * T + i];
-          if (z.lo >= z.hi) { z.lo = 0; z.hi = T; z.live = 0.f; }  // fully-masked row: uniform P, no dS
         }
-        z.off = p.lse[2 * (bh * T + i)];
-        z.ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
-        z.dl = p.delta[bh * T + i] * keep_frac;
+        const float2 ml = *reinterpret_cast<const float2*>(p.lse + 2 * (bh * T + i));
+        z.off = ml.x;
+        z.ls2 = ml.y;
+        z.dl = p.delta[bh * T + i];
         if (kDrop && (kq0 >> 5) < p.nw) z.kw = p.keep[(bh * T + i) * p.nw + (kq0 >> 5)];
-        z.vm = interval_bits32(z.lo, z.hi, kq0);  // hi <= T: keys beyond the sequence are never visible
       }
       return z;
+    };
+    auto finish_params = [&](QParams& z, int it) {
+      const int i = it * 64 + hh * 32 + lane;
+      if (i < T) {
+        if (z.lo >= z.hi) { z.lo = 0; z.hi = T; z.live = 0.f; }  // fully-masked row: uniform P, no dS
+        z.vm = interval_bits32(z.lo, z.hi, kq0);  // hi <= T: keys beyond the sequence are never visible
+      }
+      z.ls2 *= LOG2E;
+      z.dl *= keep_frac;
     };
     auto store_params = [&](int buf, const QParams& z) {
       uint8_t* base = wpar + buf * ATT_WPAR_BYTES;
@@ -557,6 +581,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     QParams cur = {};
     if (it < nq) {
       cur = load_params(it);
+      finish_params(cur, it);
       store_params(0, cur);
     }
     __syncwarp();
@@ -691,7 +716,10 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full[st]);
       // parameters of the next sub-tile into the warp's other buffer (last read during sub-tile n-1)
-      if (nx < nq) store_params(st ^ 1, zn);
+      if (nx < nq) {
+        finish_params(zn, nx);
+        store_params(st ^ 1, zn);
+      }
       cur = zn;
       __syncwarp();
       it = nx;
