@@ -265,10 +265,29 @@ def run_b200(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
-    times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
+    # ---- optional second device-resident measurement: the masked-rows-only head (same loss and gradients, the head
+    # GEMMs / CE run on the ~15 % of rows inside the MLM mask). Reported under its own key, never as `value`: the
+    # roofline fraction and the headline count the head dense over all positions, as the reference executes it.
+    ms_mr = float("nan")
+    if not args.skip_masked_rows_head:
+        from omnibiote_b200 import functional as Fn
+        trainer.head_cap = Fn.masked_rows_capacity(mbs * T, trainer.mask_prob)
+        trainer.step(dev_ids)
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for _ in range(args.steps):
+            trainer.step(dev_ids)
+        m1.record()
+        barrier()
+        ms_mr = m0.elapsed_time(m1)
+        trainer.check_head_overflow()
+        head_cap, trainer.head_cap = trainer.head_cap, 0
+
+    times = torch.tensor([ms, ms_e2e, ms_mr], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(times[0]), float(times[1])
+    ms, ms_e2e, ms_mr = float(times[0]), float(times[1]), float(times[2])
 
     if rank == 0:
         tokens_per_step = args.global_batch * T
@@ -288,7 +307,11 @@ def run_b200(args):
         roofline = {
             "kernel": "gemm_bf16_kernel (tcgen05/TMEM/TMA)", "bound": "tensor",
             "achieved": g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else None, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": (g_flops / (g_ms / 1e3) / 1e12 / peak_tf) if g_ms > 0 else None, "traffic": None,
+            "frac": (g_flops / (g_ms / 1e3) / 1e12 / peak_tf) if g_ms > 0 else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the c_fc forward shape (32768x4096x1024,
+            # ncu --set full, profiles/r01_gemm_cg2_v3.source.txt) against 344.0e6 algorithmic bytes (A + B + D):
+            # no operand is re-read from HBM
+            "traffic": 306.3e6, "traffic_shape": "32768x4096x1024 (c_fc forward), algorithmic 344.0e6 B",
             "peak_source": peak_src, "launches": len(gemm_prof), "share_of_step": g_ms / ms if ms > 0 else None,
             "step_model_flops_frac_of_2.25PF": value * ftok / world / 2.25e15,
             "step_model_flops_frac_of_measured_sustained": value * ftok / world / (peak_tf * 1e12),
@@ -308,6 +331,11 @@ def run_b200(args):
             "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": int(host_ids.numel() * 8) * world,
                     "d2h_bytes_per_step": 4 * world},
             "gpu_launches": launches, "clocks": clock_info, "roofline": roofline, "loss": last_loss,
+            "masked_rows_head": None if ms_mr != ms_mr else {
+                "value": tokens_per_step * args.steps / (ms_mr / 1e3), "unit": "tokens/s", "head_rows": head_cap,
+                "of_rows": mbs * T,
+                "note": "same step with the head GEMMs / CE restricted to the rows inside the MLM mask (identical loss "
+                        "and gradients); reported separately, not used for `value`, `e2e` or the roofline"},
             "cpu_baseline": None if cpu_tps is None else {
                 "value": cpu_tps, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
                 "sample": "2 steps of 2 x 1024 tokens (oracle port, torch CPU bf16, all host threads)"},
@@ -327,6 +355,7 @@ def main():
     ap.add_argument("--mini-batch-size", type=int, default=32)
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-masked-rows-head", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

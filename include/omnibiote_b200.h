@@ -149,6 +149,20 @@ int obt_mlm_mask(const long long* ids, long long* masked_ids, unsigned char* mas
                  unsigned long long seed, unsigned long long offset, long long pad_token, long long eos_token,
                  long long mask_token, cudaStream_t stream);
 
+/* ---- masked-rows-only head (optional path of the training step): d loss / d logits of train_encoder.py:301-305 is
+ * exactly zero outside the MLM mask, so ln_f's output rows inside the mask are compacted, the head GEMM, the CE and
+ * their backward run on those rows only, and the input gradient is scattered back (zeros elsewhere). Results are
+ * identical to the dense path; the dense path stays the default (it is what the reference executes).
+ * obt_compact_rows: idx[cap] = rows with mask != 0 in row order, -1 padded; targets_c / valid_c per slot;
+ *                   meta = {count, count > cap}. */
+int obt_compact_rows(const unsigned char* mask, const long long* targets, long long M, int cap, int* idx,
+                     long long* targets_c, unsigned char* valid_c, int* meta, cudaStream_t stream);
+int obt_gather_rows(const void* src, long long lds, const int* idx, void* dst, long long ldd, int n_slots, int C,
+                    cudaStream_t stream);
+/* dst [M, C] contiguous: zero-filled, then dst[idx[s]] = src[s] for idx[s] >= 0 */
+int obt_scatter_rows(const void* src, long long lds, const int* idx, void* dst, long long ldd, long long M, int n_slots,
+                     int C, cudaStream_t stream);
+
 /* ---- MLM loss (train_encoder.py:301-305) over materialised logits ----------------------------------------------
  * scalars (device fp32[4]): [0] loss, [1] number of masked tokens, [2] d loss / d CE_t. row_mask: uint8 [M] or NULL. */
 int obt_ce_fwd(const void* logits, long long ld, const long long* targets, const unsigned char* row_mask, float* lse,

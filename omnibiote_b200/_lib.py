@@ -48,6 +48,9 @@ SIGNATURES = {
     "obt_mask_from_intervals": (i32, [vp, vp, vp, i32, i32, vp]),
     "obt_mask_compress": (i32, [vp, i64, i64, vp, vp, vp, i32, i32, vp]),
     "obt_mlm_mask": (i32, [vp, vp, vp, i64, f32, u64, u64, i64, i64, i64, vp]),
+    "obt_compact_rows": (i32, [vp, vp, i64, i32, vp, vp, vp, vp, vp]),
+    "obt_gather_rows": (i32, [vp, i64, vp, vp, i64, i32, i32, vp]),
+    "obt_scatter_rows": (i32, [vp, i64, vp, vp, i64, i64, i32, i32, vp]),
     "obt_ce_fwd": (i32, [vp, i64, vp, vp, vp, vp, vp, i64, i32, f32, vp]),
     "obt_ce_bwd": (i32, [vp, i64, vp, vp, vp, vp, f32, i64, i32, vp]),
     "obt_opt_chunk_elems": (i32, []),

@@ -221,3 +221,126 @@ extern "C" int obt_mlm_mask(const long long* ids, long long* masked_ids, unsigne
                                                                         pad_token, eos_token, mask_token);
   return check_launch("mlm_mask");
 }
+
+// ---------------------------------------------------------------------------------------------
+// Row compaction for the masked-rows-only head (d loss / d logits is exactly zero on the ~85 % of
+// rows outside the MLM mask, so the head GEMMs, the CE and their backward only need the masked rows).
+//   compact_rows : stable list of the rows with mask != 0 -> idx[0..count), padded with -1 up to `cap`; the targets of
+//                  those rows and a validity byte per slot; meta = {count, overflow (count > cap)}.
+//   gather_rows  : dst[s] = src[idx[s]] (zeros for idx < 0);  scatter_rows : dst = 0, then dst[idx[s]] = src[s].
+// ---------------------------------------------------------------------------------------------
+namespace obt {
+
+constexpr int COMPACT_THREADS = 1024;
+
+__global__ void __launch_bounds__(COMPACT_THREADS, 1)
+compact_rows_kernel(const unsigned char* __restrict__ mask, const long long* __restrict__ targets, long long M, int cap,
+                    int* __restrict__ idx, long long* __restrict__ tgt_c, unsigned char* __restrict__ valid_c,
+                    int* __restrict__ meta) {
+  __shared__ int warp_tot[COMPACT_THREADS / 32];
+  __shared__ int base_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) base_s = 0;
+  __syncthreads();
+  // chunks of COMPACT_THREADS rows, processed in order so that the output order is the row order (deterministic sums)
+  for (long long c0 = 0; c0 < M; c0 += COMPACT_THREADS) {
+    const long long i = c0 + tid;
+    const bool m = i < M && mask[i] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, m);
+    const int before = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int wbase = 0, total = 0;
+    for (int w = 0; w < COMPACT_THREADS / 32; ++w) {
+      const int t = warp_tot[w];
+      if (w < warp) wbase += t;
+      total += t;
+    }
+    const int base = base_s;
+    if (m) {
+      const int slot = base + wbase + before;
+      if (slot < cap) {
+        idx[slot] = static_cast<int>(i);
+        tgt_c[slot] = targets[i];
+        valid_c[slot] = 1;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) base_s = base + total;
+    __syncthreads();
+  }
+  const int count = base_s;
+  for (int s = count + tid; s < cap; s += COMPACT_THREADS) {
+    idx[s] = -1;
+    tgt_c[s] = 0;
+    valid_c[s] = 0;
+  }
+  if (tid == 0) {
+    meta[0] = count;
+    meta[1] = count > cap ? 1 : 0;
+  }
+}
+
+// one warp per destination row, 16-byte chunks
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, long long lds, const int* __restrict__ idx,
+                                   __nv_bfloat16* __restrict__ dst, long long ldd, int n_slots, int C) {
+  const int warps = blockDim.x >> 5;
+  const int s = blockIdx.x * warps + (threadIdx.x >> 5);
+  if (s >= n_slots) return;
+  const int lane = threadIdx.x & 31;
+  const int r = idx[s];
+  for (int c = lane; c < C / 8; c += 32) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r >= 0) v = reinterpret_cast<const uint4*>(src + static_cast<long long>(r) * lds)[c];
+    reinterpret_cast<uint4*>(dst + static_cast<long long>(s) * ldd)[c] = v;
+  }
+}
+
+__global__ void scatter_rows_kernel(const __nv_bfloat16* __restrict__ src, long long lds, const int* __restrict__ idx,
+                                    __nv_bfloat16* __restrict__ dst, long long ldd, int n_slots, int C) {
+  const int warps = blockDim.x >> 5;
+  const int s = blockIdx.x * warps + (threadIdx.x >> 5);
+  if (s >= n_slots) return;
+  const int lane = threadIdx.x & 31;
+  const int r = idx[s];
+  if (r < 0) return;
+  for (int c = lane; c < C / 8; c += 32)
+    reinterpret_cast<uint4*>(dst + static_cast<long long>(r) * ldd)[c] =
+        reinterpret_cast<const uint4*>(src + static_cast<long long>(s) * lds)[c];
+}
+
+}  // namespace obt
+
+extern "C" int obt_compact_rows(const unsigned char* mask, const long long* targets, long long M, int cap, int* idx,
+                                long long* targets_c, unsigned char* valid_c, int* meta, cudaStream_t stream) {
+  OBT_REQUIRE(mask && targets && idx && targets_c && valid_c && meta, "obt_compact_rows: null pointer");
+  OBT_REQUIRE(M > 0 && M < (1ll << 31) && cap > 0, "obt_compact_rows: bad M=%lld cap=%d", M, cap);
+  obt::compact_rows_kernel<<<1, obt::COMPACT_THREADS, 0, stream>>>(mask, targets, M, cap, idx, targets_c, valid_c, meta);
+  return check_launch("compact_rows");
+}
+
+extern "C" int obt_gather_rows(const void* src, long long lds, const int* idx, void* dst, long long ldd, int n_slots,
+                               int C, cudaStream_t stream) {
+  OBT_REQUIRE(src && idx && dst, "obt_gather_rows: null pointer");
+  OBT_REQUIRE(C % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 && n_slots > 0, "obt_gather_rows: C=%d must be a multiple of 8", C);
+  const int warps = 8;
+  obt::gather_rows_kernel<<<(n_slots + warps - 1) / warps, warps * 32, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(src), lds, idx, static_cast<__nv_bfloat16*>(dst), ldd, n_slots, C);
+  return check_launch("gather_rows");
+}
+
+extern "C" int obt_scatter_rows(const void* src, long long lds, const int* idx, void* dst, long long ldd, long long M,
+                                int n_slots, int C, cudaStream_t stream) {
+  OBT_REQUIRE(src && idx && dst, "obt_scatter_rows: null pointer");
+  OBT_REQUIRE(C % 8 == 0 && lds % 8 == 0 && ldd == C && n_slots > 0 && M > 0,
+              "obt_scatter_rows: C=%d must be a multiple of 8 and dst contiguous", C);
+  cudaError_t e = cudaMemsetAsync(dst, 0, static_cast<size_t>(M) * C * 2, stream);
+  if (e != cudaSuccess) {
+    set_last_error("obt_scatter_rows: memset: %s", cudaGetErrorString(e));
+    return OBT_ERR_CUDA;
+  }
+  const int warps = 8;
+  obt::scatter_rows_kernel<<<(n_slots + warps - 1) / warps, warps * 32, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(src), lds, idx, static_cast<__nv_bfloat16*>(dst), ldd, n_slots, C);
+  return check_launch("scatter_rows");
+}

@@ -242,6 +242,56 @@ class HeadLossFunction(torch.autograd.Function):
         return dx, (None if acc else dg), dw, None, None, None, None
 
 
+class HeadLossMaskedRowsFunction(torch.autograd.Function):
+    """HeadLossFunction restricted to the rows inside the MLM mask (optional; the dense path is the default).
+
+    d loss / d logits of train_encoder.py:301-305 is exactly zero outside the mask, so ln_f's rows
+    inside the mask are compacted into a fixed-capacity buffer [cap, C] (no host synchronisation: unused slots are
+    zero rows with a zero gradient), the head GEMM, the CE and both backward GEMMs run on cap rows instead of M, and
+    d z is scattered back with zeros elsewhere. Loss and gradients equal the dense path's (same rows, same arithmetic;
+    only the fp32 summation order of the weight gradient's reduction differs). `meta` = {count, overflow}: overflow
+    != 0 means more masked rows than `cap` and the caller must redo the micro-batch with the dense path.
+    """
+
+    @staticmethod
+    def forward(ctx, x, gamma, weight, div, targets, loss_mask, n_acc, cap):
+        emb, z, mean, rstd = ops.layernorm_fwd(x, gamma, readout_div=div)
+        del emb
+        idx, tgt_c, valid_c, meta = ops.compact_rows(loss_mask, targets, cap)
+        zc = ops.gather_rows(z, idx)
+        del z
+        logits = ops.gemm(zc, weight)
+        scalars, lse, tok, row_mask, tgt = ops.ce_fwd(logits, tgt_c, valid_c, n_acc)
+        ops.ce_bwd_(logits, tgt, row_mask, lse, scalars, 1.0)
+        ctx.save_for_backward(x, gamma, weight, mean, rstd, zc, logits, idx)
+        ctx.div = div
+        ctx.params = (gamma, weight)
+        ctx.mark_non_differentiable(scalars, meta)
+        loss = scalars[0].to(torch.bfloat16)
+        return loss, scalars, meta
+
+    @staticmethod
+    def backward(ctx, dloss, _dscalars, _dmeta):
+        x, gamma, weight, mean, rstd, zc, dlogits, idx = ctx.saved_tensors
+        pg, pw = ctx.params
+        dw = _wgrad(dlogits, zc, pw)
+        dzc = ops.gemm(dlogits, weight, b_mn=True)
+        dz = ops.scatter_rows(dzc, idx, x.shape[0])
+        acc = _DIRECT_GRAD and pg.grad is not None
+        dx, dg = ops.layernorm_bwd(dz, x, gamma, mean, rstd, dgamma=pg.grad if acc else None, accumulate_dgamma=acc,
+                                   dy_div=ctx.div)
+        _grads_final(ctx.params)
+        return dx, (None if acc else dg), dw, None, None, None, None, None
+
+
+def masked_rows_capacity(n_rows: int, mask_prob: float, sigmas: float = 8.0) -> int:
+    """Rows to reserve for the masked-rows-only head: mean + `sigmas` standard deviations of Binomial(n_rows, p),
+    rounded up to the GEMM's 256-row tile."""
+    import math
+    want = n_rows * mask_prob + sigmas * math.sqrt(max(n_rows * mask_prob * (1.0 - mask_prob), 1.0))
+    return min(-(-n_rows // 256) * 256, int(-(-want // 256)) * 256)
+
+
 class PoolFunction(torch.autograd.Function):
     """encode() pooling over the token axis: mean / max  (model.py:269-278)."""
 

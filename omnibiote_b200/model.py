@@ -224,16 +224,27 @@ class OmniBioTA(nn.Module):
             return emb
 
     # ------------------------------------------------------------------------------------------------------------
-    def mlm_loss(self, masked_idx, targets, loss_mask, attn_mask=None, n_accum: int = 1):
+    def mlm_loss(self, masked_idx, targets, loss_mask, attn_mask=None, n_accum: int = 1, masked_rows_cap: int = 0):
         """Fused training-step front half: forward + head + masked-LM loss of train_encoder.py:296-305.
 
         Equivalent to ``ce = F.cross_entropy(model(masked_idx, attn_mask).view(-1, V), targets.view(-1),
         reduction="none") / n_accum; ce *= loss_mask.view(-1).float(); loss = ce.sum() / loss_mask.sum()`` with the
         reference's bf16 rounding points, but ln_f, the readout scaling, the head GEMM and the CE forward/backward
         run as one schedule. Returns (loss [bf16 scalar, differentiable], scalars [fp32: loss, n_masked, dCE]).
+
+        masked_rows_cap > 0 selects the masked-rows-only head (functional.HeadLossMaskedRowsFunction): same loss and
+        gradients, the head runs on at most that many rows; ``self.head_rows_meta`` (device int32 {count, overflow})
+        tells whether the capacity sufficed.
         """
         x = self._trunk(masked_idx, attn_mask)
         b, t, C = x.shape
+        if masked_rows_cap > 0:
+            loss, scalars, meta = Fn.HeadLossMaskedRowsFunction.apply(
+                x.reshape(b * t, C), self.transformer.ln_f.weight, self.lm_head.weight,
+                float(self.lm_head.readout_div()), targets.reshape(-1), loss_mask.reshape(-1), float(n_accum),
+                int(masked_rows_cap))
+            self.head_rows_meta = meta
+            return loss, scalars
         loss, scalars = Fn.HeadLossFunction.apply(
             x.reshape(b * t, C), self.transformer.ln_f.weight, self.lm_head.weight, float(self.lm_head.readout_div()),
             targets.reshape(-1), loss_mask.reshape(-1), float(n_accum))

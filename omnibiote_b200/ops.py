@@ -361,6 +361,42 @@ def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, ke
     return dqkv
 
 
+def compact_rows(row_mask: torch.Tensor, targets: torch.Tensor, cap: int):
+    """Rows with mask != 0, in row order: (idx int32 [cap] (-1 padded), targets_c int64 [cap], valid_c uint8 [cap],
+    meta int32 [2] = {count, overflow})."""
+    row_mask = row_mask.reshape(-1).to(torch.uint8).contiguous()
+    targets = targets.reshape(-1).contiguous()
+    _req(targets, "targets", torch.int64)
+    dev = row_mask.device
+    idx = torch.empty(cap, dtype=torch.int32, device=dev)
+    tgt = torch.empty(cap, dtype=torch.int64, device=dev)
+    valid = torch.empty(cap, dtype=torch.uint8, device=dev)
+    meta = torch.empty(2, dtype=torch.int32, device=dev)
+    rc = _lib.load().obt_compact_rows(row_mask.data_ptr(), targets.data_ptr(), row_mask.numel(), int(cap), idx.data_ptr(),
+                                      tgt.data_ptr(), valid.data_ptr(), meta.data_ptr(), _stream())
+    _lib.check(rc, "obt_compact_rows")
+    return idx, tgt, valid, meta
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    src, lds = _mat(src, "gather source")
+    out = torch.empty((idx.numel(), src.shape[1]), dtype=torch.bfloat16, device=src.device)
+    rc = _lib.load().obt_gather_rows(src.data_ptr(), lds, idx.data_ptr(), out.data_ptr(), out.shape[1], idx.numel(),
+                                     src.shape[1], _stream())
+    _lib.check(rc, "obt_gather_rows")
+    return out
+
+
+def scatter_rows(src: torch.Tensor, idx: torch.Tensor, M: int) -> torch.Tensor:
+    """out [M, C] = 0 except out[idx[s]] = src[s]."""
+    src, lds = _mat(src, "scatter source")
+    out = torch.empty((M, src.shape[1]), dtype=torch.bfloat16, device=src.device)
+    rc = _lib.load().obt_scatter_rows(src.data_ptr(), lds, idx.data_ptr(), out.data_ptr(), out.shape[1], M, idx.numel(),
+                                      src.shape[1], _stream())
+    _lib.check(rc, "obt_scatter_rows")
+    return out
+
+
 def ce_fwd(logits: torch.Tensor, targets: torch.Tensor, row_mask: torch.Tensor | None, n_acc: float):
     """Returns (scalars[4] fp32 device: loss, count, dloss/dCE; lse [M]; tok_loss [M])."""
     logits, ld = _mat(logits, "logits")

@@ -43,7 +43,7 @@ class MLMTrainer:
     def __init__(self, model, *, global_batch: int, mini_batch_size: int, ctx_len: int, lr: float = 1e-2,
                  weight_decay: float = 1e-2, betas=(0.9, 0.999), eps: float = 1e-8, token_budget: float = 250e9,
                  use_padding: bool = False, mask_prob: float = 0.15, max_grad_norm: float = 1.0, force_lr: bool = False,
-                 process_group=None):
+                 process_group=None, masked_rows_head: bool = False):
         self.model = model
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
@@ -58,6 +58,11 @@ class MLMTrainer:
         self.mask_prob = mask_prob
         self.max_grad_norm = max_grad_norm
         self.n_head = model.transformer.h[0].attn.n_head
+        # optional masked-rows-only head (same loss and gradients; see functional.HeadLossMaskedRowsFunction): capacity
+        # = mean + 8 sigma of the Binomial number of masked rows; an overflow is counted on the device and raises at
+        # the next check_head_overflow()
+        self.head_cap = Fn.masked_rows_capacity(mini_batch_size * ctx_len, mask_prob) if masked_rows_head else 0
+        self.head_overflow = torch.zeros(1, dtype=torch.int32, device=next(model.parameters()).device)
 
         # train_encoder.py:194-201
         total_iters = max(1, int(token_budget / (self.world * self.batch_size * ctx_len)))
@@ -87,7 +92,10 @@ class MLMTrainer:
                     m = mask[j * mbs:(j + 1) * mbs]
                     lo, hi = ops.doc_mask_intervals(y, EOS_TOKEN, self.use_padding)
                     spec = ops.MaskSpec(None, mbs, H, T, lo, hi)
-                    loss, scalars = self.model.mlm_loss(x, y, m, attn_mask=spec, n_accum=self.n_accum)
+                    loss, scalars = self.model.mlm_loss(x, y, m, attn_mask=spec, n_accum=self.n_accum,
+                                                        masked_rows_cap=self.head_cap)
+                    if self.head_cap:
+                        self.head_overflow += self.model.head_rows_meta[1:2]
                     if j == self.n_accum - 1:
                         self.buckets.arm()  # overlap the all-reduce with the last micro-batch's backward
                     loss.backward()
@@ -99,3 +107,8 @@ class MLMTrainer:
         self.scheduler.step()
         self.trained_tokens += self.global_batch * T
         return self.loss_sum
+
+    def check_head_overflow(self) -> None:
+        """Host check (synchronises): raises if any micro-batch had more masked rows than the head capacity."""
+        if self.head_cap and int(self.head_overflow.item()) != 0:
+            raise RuntimeError("omnibiote_b200: masked-rows head capacity exceeded; use masked_rows_head=False")

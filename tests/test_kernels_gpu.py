@@ -247,3 +247,25 @@ def test_fused_adamw_matches_torch_bf16_foreach(golden):
         assert max_abs(st["exp_avg"], a["m"][s]) <= 2 ** -7 * float(a["m"][s].abs().max())  # <= 1 bf16 ulp
         assert max_abs(st["exp_avg_sq"], a["v"][s]) <= 2 ** -7 * float(a["v"][s].abs().max())
         assert max_abs(p, a["p"][s]) <= 2 ** -7 * float(a["p"][s].abs().max())
+
+
+def test_row_compaction_gather_scatter():
+    ops = _ops()
+    torch.manual_seed(0)
+    M, C, cap = 5000, 256, 1024
+    mask = torch.rand(M, device="cuda") < 0.15
+    tgt = torch.randint(0, 1000, (M,), device="cuda")
+    idx, tgt_c, valid_c, meta = ops.compact_rows(mask, tgt, cap)
+    want = mask.nonzero().flatten()
+    n = want.numel()
+    assert meta.tolist() == [n, 0]
+    assert torch.equal(idx[:n].long(), want) and bool((idx[n:] == -1).all())          # row order preserved, -1 padded
+    assert torch.equal(tgt_c[:n], tgt[want]) and torch.equal(valid_c.bool(), torch.arange(cap, device="cuda") < n)
+    x = torch.randn(M, C, device="cuda").to(BF)
+    g = ops.gather_rows(x, idx)
+    assert torch.equal(g[:n], x[want]) and float(g[n:].abs().max()) == 0.0
+    back = ops.scatter_rows(g, idx, M)
+    assert torch.equal(back[want], x[want]) and float(back[~mask].abs().max()) == 0.0
+    # capacity too small: flagged, never written out of bounds
+    idx2, _, _, meta2 = ops.compact_rows(mask, tgt, 64)
+    assert meta2.tolist() == [n, 1] and torch.equal(idx2.long(), want[:64])

@@ -84,7 +84,7 @@ def test_encode_all_methods(golden, name):
 
 
 @pytest.mark.parametrize("name", ["bf16_h2", "bf16_h1"])
-@pytest.mark.parametrize("path", ["dropin", "fused"])
+@pytest.mark.parametrize("path", ["dropin", "fused", "masked_rows"])
 def test_mlm_loss_and_gradients(golden, name, path):
     """train_encoder.py:296-308 on the same weights / batch / MLM mask as the golden reference run (n_accum = 2)."""
     c = golden(name)
@@ -97,8 +97,12 @@ def test_mlm_loss_and_gradients(golden, name, path):
         loss = torch.nn.functional.cross_entropy(logits.view(-1, logits.size(-1)), ids.view(-1), reduction="none") / 2
         loss *= lm.view(-1).float()
         loss = loss.sum() / lm.view(-1).sum()
-    else:
+    elif path == "fused":
         loss, _ = model.mlm_loss(masked, ids, lm, attn_mask=mask, n_accum=2)
+    else:  # head restricted to the rows inside the MLM mask: same loss, same gradients
+        cap = -(-int(lm.sum()) // 8) * 8 + 8
+        loss, _ = model.mlm_loss(masked, ids, lm, attn_mask=mask, n_accum=2, masked_rows_cap=cap)
+        assert model.head_rows_meta.tolist() == [int(lm.sum()), 0]
     loss.backward()
     ulp = 2 ** -7 * float(c["loss"])
     assert abs(float(loss) - float(c["loss"])) <= ulp, (float(loss), float(c["loss"]))
