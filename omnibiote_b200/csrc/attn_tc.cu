@@ -42,8 +42,11 @@ template <bool kDrop>
 __global__ void __launch_bounds__(ATT_FWD_THREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                    const AttnTcParams p, int C) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128B-swizzle atoms) is requested from the toolchain, so every smem address below is a
+  // link-time constant instead of a live register (the run-time round-up cost registers / spill reloads in the loops)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0u) __trap();
   uint8_t* sQ = smem + AttnFwdSmem::Q_OFF;
   uint8_t* sK = smem + AttnFwdSmem::K_OFF;
   uint8_t* sV = smem + AttnFwdSmem::V_OFF;

@@ -64,8 +64,11 @@ template <bool kDrop>
 __global__ void __launch_bounds__(ATT_THREADS_BWD, 1)
 attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16* __restrict__ qkv, long long ld,
                   const __nv_bfloat16* __restrict__ dy, long long lddy, const AttnTcParams p, int C) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128B-swizzle atoms) is requested from the toolchain, so every smem address below is a
+  // link-time constant instead of a live register (the run-time round-up cost registers / spill reloads in the loops)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0u) __trap();
   uint8_t* sK = smem + AttnDqSmem::K_OFF;
   uint8_t* sV = smem + AttnDqSmem::V_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnDqSmem::BAR_OFF);
@@ -355,6 +358,12 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
 // =============================================================================================
 constexpr uint32_t ATT_SUB_BYTES = 64 * 128 * 2;  // one [64 rows x 128] bf16 tile = two 8 KB swizzle sub-tiles
 constexpr int ATT_QDO_STAGES = 4;
+// 12 warps: warpgroup 0 = {TMA producer, MMA issuer, 2 idle}, warpgroups 1-2 = the 8 compute warps. Three warps share
+// each scheduler's 16 K registers (168 per thread at launch); v6 with 10 warps spilled in the compute loop and
+// reloaded the spills on the critical path (7 % of all stall samples, profiles/r01_attn_v7_bwd.source.txt). With the
+// roles aligned to warpgroups, warpgroup 0 returns registers (setmaxnreg.dec) and the compute warps take them.
+constexpr int ATT_DKV_THREADS = 384;
+constexpr int ATT_DKV_FIRST_COMPUTE_WARP = 4;
 // per warp and buffer: 32 x float2 {-(max+lsum)*log2e, delta*(1-p)} + 32 x int2 {lo,hi} + 32 x float2 {max, lsum*log2e}
 // + 32 x float live + 32 keep words + 32 visibility words (which of the warp's 32 keys each query sees)
 constexpr uint32_t ATT_WPAR_BYTES = 1152;
@@ -370,11 +379,14 @@ struct AttnDkvSmem {
 };
 
 template <bool kDrop>
-__global__ void __launch_bounds__(ATT_THREADS_BWD, 1)
+__global__ void __launch_bounds__(ATT_DKV_THREADS, 1)
 attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_q64,
                    const __grid_constant__ CUtensorMap tm_dy64, const AttnTcParams p, int C) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128B-swizzle atoms) is requested from the toolchain, so every smem address below is a
+  // link-time constant instead of a live register (the run-time round-up cost registers / spill reloads in the loops)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0u) __trap();
   uint8_t* sK = smem + AttnDkvSmem::K_OFF;
   uint8_t* sV = smem + AttnDkvSmem::V_OFF;
   uint8_t* sQ = smem + AttnDkvSmem::Q_OFF;
@@ -454,13 +466,13 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   // shuffled from lane 0 so that the compiler knows the value is warp-uniform: tcgen05 operands then go through
   // uniform registers directly instead of a per-lane R2UR waterfall loop around every MMA
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tmem_slot), 0);
-  const unsigned int rel0 = s_rel[0], rel1 = s_rel[1], rel2 = s_rel[2], rel3 = s_rel[3];
-  auto relevant = [&](int it) -> bool {
-    const unsigned int w = (it >> 5) == 0 ? rel0 : (it >> 5) == 1 ? rel1 : (it >> 5) == 2 ? rel2 : rel3;
-    return (w >> (it & 31)) & 1u;
-  };
+  // read from shared memory at every use: held in registers these words were live across the role split and got
+  // spilled, with the reloads on the compute loop's critical path
+  auto relevant = [&](int it) -> bool { return (s_rel[it >> 5] >> (it & 31)) & 1u; };
 
-  if (warp == 0) {
+  if (warp < ATT_DKV_FIRST_COMPUTE_WARP) {
+   reg_dealloc<56>();
+   if (warp == 0) {
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
@@ -512,9 +524,11 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       }
       __syncwarp();
     }
+   }
   } else {
+    reg_alloc<224>();
     const int q = warp & 3;
-    const int hh = (warp - 2) >> 2;  // two threads per key row: query columns [32*hh, +32) of every 64-query sub-tile
+    const int hh = (warp - ATT_DKV_FIRST_COMPUTE_WARP) >> 2;  // two threads per key row: query columns [32*hh, +32)
     const int r = q * 32 + lane;     // key row within the tile
     const int j = j0 + r;
     const bool key_ok = j < T;
@@ -525,7 +539,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const float keep_frac = kDrop ? 1.0f - p.drop_p : 1.0f;
     const float sc2 = p.scale * LOG2E;
     const uint32_t mybit = 1u << keep_bit_pos(lane);  // this key's bit inside the keep word of its 32-key group
-    uint8_t* wpar = sPar + (warp - 2) * 2 * ATT_WPAR_BYTES;
+    uint8_t* wpar = sPar + (warp - ATT_DKV_FIRST_COMPUTE_WARP) * 2 * ATT_WPAR_BYTES;
     // Per-query parameters of THIS warp's 32 query columns (lane = query), software-pipelined: the global loads for
     // the next relevant sub-tile are issued before the math of the current one and staged in the warp's other smem
     // buffer afterwards; the math reads them back as warp-wide broadcasts.
@@ -851,8 +865,8 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
   rc = check_launch("attn_tc_dq");
   if (rc) return rc;
   if (drop_p > 0.f)
-    attn_tc_dkv_kernel<true><<<grid, ATT_THREADS_BWD, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
+    attn_tc_dkv_kernel<true><<<grid, ATT_DKV_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
   else
-    attn_tc_dkv_kernel<false><<<grid, ATT_THREADS_BWD, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
+    attn_tc_dkv_kernel<false><<<grid, ATT_DKV_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
   return check_launch("attn_tc_dkv");
 }
