@@ -39,6 +39,8 @@ void obt_clear_descriptor_cache(void);
  *           2 aux_out = U = rb(acc); D = rb(gelu(U))   fused_gelu (model.py:23-25)
  *           3 D = rb(rb(acc) * gelu'(aux_in))          backward of fused_gelu, aux_in = U
  *           5 D = rb(aux_in + dropout(rb(acc)))        resid_dropout + residual (model.py:151,167,179-180)
+ *           8 D = aux_in[row] ? rb(acc) : 0 with aux_in a uint8 row mask [M]: MLM head whose unmasked rows are never
+ *             read (zero loss weight and gradient, train_encoder.py:301-305); pairs with obt_ce_bwd(unmasked_rows_zero)
  *           7 D = rb(rotary(rb(acc))) on columns < rope_cols: apply_rotary_emb (model.py:39-50,108) fused into
  *             c_attn; rope_cos / rope_sin are fp32 [rope_T, rope_head_dim/2] tables (position = row % rope_T),
  *             rope_sin = NULL for the real bf16 freqs_cis buffer a bf16 model carries (cosine scaling)
@@ -167,9 +169,10 @@ int obt_scatter_rows(const void* src, long long lds, const int* idx, void* dst, 
  * scalars (device fp32[4]): [0] loss, [1] number of masked tokens, [2] d loss / d CE_t. row_mask: uint8 [M] or NULL. */
 int obt_ce_fwd(const void* logits, long long ld, const long long* targets, const unsigned char* row_mask, float* lse,
                float* tok_loss, float* scalars, long long M, int V, float n_acc, cudaStream_t stream);
-/* overwrites logits with d loss / d logits (exact zeros on unmasked rows) */
+/* overwrites logits with d loss / d logits (exact zeros on unmasked rows). unmasked_rows_zero != 0: the caller
+ * guarantees those rows already hold zeros (head GEMM with epilogue 8), so they are neither read nor written. */
 int obt_ce_bwd(void* logits, long long ld, const long long* targets, const unsigned char* row_mask, const float* lse,
-               const float* scalars, float upstream, long long M, int V, cudaStream_t stream);
+               const float* scalars, float upstream, long long M, int V, int unmasked_rows_zero, cudaStream_t stream);
 
 /* ---- clip_grad_norm_ (train_encoder.py:316) + MuAdamW step (train_encoder.py:199,317) --------------------------
  * metas: device array of {void* p, g, m, v; int64 numel; float lr, wd} (obt_opt_meta_bytes() each);

@@ -52,7 +52,7 @@ SIGNATURES = {
     "obt_gather_rows": (i32, [vp, i64, vp, vp, i64, i32, i32, vp]),
     "obt_scatter_rows": (i32, [vp, i64, vp, vp, i64, i64, i32, i32, vp]),
     "obt_ce_fwd": (i32, [vp, i64, vp, vp, vp, vp, vp, i64, i32, f32, vp]),
-    "obt_ce_bwd": (i32, [vp, i64, vp, vp, vp, vp, f32, i64, i32, vp]),
+    "obt_ce_bwd": (i32, [vp, i64, vp, vp, vp, vp, f32, i64, i32, i32, vp]),
     "obt_opt_chunk_elems": (i32, []),
     "obt_opt_meta_bytes": (i32, []),
     "obt_grad_norm": (i32, [vp, vp, vp, i32, f32, f32, vp, vp, vp]),

@@ -369,7 +369,8 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   OBT_REQUIRE(A && B && D, "obt_gemm_bf16: null operand");
   OBT_REQUIRE(M > 0 && N > 0 && K > 0, "obt_gemm_bf16: empty problem M=%lld N=%lld K=%lld", M, N, K);
   OBT_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "obt_gemm_bf16: dims exceed int32");
-  OBT_REQUIRE(((epilogue >= EPI_PLAIN && epilogue <= EPI_RESID_DROPOUT) || epilogue == EPI_ROPE) &&
+  OBT_REQUIRE(((epilogue >= EPI_PLAIN && epilogue <= EPI_RESID_DROPOUT) || epilogue == EPI_ROPE ||
+               epilogue == EPI_ROWMASK) &&
                   epilogue != EPI_PARTIAL,
               "obt_gemm_bf16: bad epilogue %d", epilogue);
   if (epilogue == EPI_ROPE)
@@ -377,7 +378,7 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
                     (reinterpret_cast<uintptr_t>(rope_cos) & 15) == 0 && (reinterpret_cast<uintptr_t>(rope_sin) & 15) == 0,
                 "obt_gemm_bf16: rotary epilogue needs 16-byte aligned fp32 tables, head_dim %% 8 == 0 (got %d), "
                 "rope_cols %% 8 == 0 (got %d)", rope_head_dim, rope_cols);
-  if (epilogue == EPI_RESID || epilogue == EPI_GELU_BWD || epilogue == EPI_RESID_DROPOUT)
+  if (epilogue == EPI_RESID || epilogue == EPI_GELU_BWD || epilogue == EPI_RESID_DROPOUT || epilogue == EPI_ROWMASK)
     OBT_REQUIRE(aux_in != nullptr, "obt_gemm_bf16: epilogue %d needs aux_in", epilogue);
   if (epilogue == EPI_GELU) OBT_REQUIRE(aux_out != nullptr, "obt_gemm_bf16: GELU epilogue needs aux_out");
 
@@ -419,7 +420,7 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   p.rope_cols = rope_cols;
   auto aligned16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
   p.vec_ok = (N % 8 == 0) && (ldd % 8 == 0) && aligned16(D) &&
-             (aux_in == nullptr || (ld_aux_in % 8 == 0 && aligned16(aux_in))) &&
+             (aux_in == nullptr || epilogue == EPI_ROWMASK || (ld_aux_in % 8 == 0 && aligned16(aux_in))) &&
              (aux_out == nullptr || (ld_aux_out % 8 == 0 && aligned16(aux_out)));
 
   // split-K when the output tile grid cannot fill the machine and the reduction is long (wgrad shapes).

@@ -25,6 +25,9 @@ enum : int {
   EPI_GELU_EAGER = 6,     // internal: EPI_GELU with one bf16 rounding per primitive (gelu_mode = 1)
   EPI_ROPE = 7,           // D = rb(rotary(rb(acc))) on columns < rope_cols (q | k of the fused c_attn output):
                           // apply_rotary_emb (model.py:39-50,108) fused into the c_attn GEMM
+  EPI_ROWMASK = 8,        // D = row_mask[row] ? rb(acc) : 0 with aux_in = uint8 [M]: the MLM head's logits of rows
+                          // outside the loss mask are never read (their loss weight and gradient are exactly zero,
+                          // train_encoder.py:301-305), so the zeros d loss / d logits needs there are stored right away
 };
 
 struct GemmParams {
@@ -238,6 +241,12 @@ __device__ __noinline__ void epilogue_segment_slow(const GemmParams& p, uint4 w,
       rope8(v, cs, sn, p.rope_sin != nullptr, false);
     }
   }
+  if constexpr (EPI == EPI_ROWMASK) {
+    if (reinterpret_cast<const unsigned char*>(p.aux_in)[grow] == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    }
+  }
   epilogue_math<EPI>(p, v, a, u, grow, gcol);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -316,6 +325,12 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
               if constexpr (EPI == EPI_ROPE) {
                 if (gcol < p.rope_cols) rope8(v, rc[it], rs[it], p.rope_sin != nullptr, false);
               }
+              if constexpr (EPI == EPI_ROWMASK) {
+                if (reinterpret_cast<const unsigned char*>(p.aux_in)[grow] == 0) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                }
+              }
               epilogue_math<EPI>(p, v, a, u, grow, gcol);
               if constexpr (EpiTraits<EPI>::kAuxOut)
                 *reinterpret_cast<uint4*>(p.aux_out + grow * p.ld_aux_out + gcol) = pack8f(u);
@@ -345,6 +360,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const GemmParams& p, uint32_t
       epilogue_chunks<EPI_RESID_DROPOUT>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end);
       break;
     case EPI_ROPE: epilogue_chunks<EPI_ROPE>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
+    case EPI_ROWMASK: epilogue_chunks<EPI_ROWMASK>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
     default: epilogue_chunks<EPI_GELU_EAGER>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
   }
 }

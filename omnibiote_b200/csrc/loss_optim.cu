@@ -110,10 +110,11 @@ __global__ void ce_reduce_kernel(const float* __restrict__ tok_loss, const unsig
 // Written in place over the logits buffer.
 __global__ void ce_bwd_kernel(__nv_bfloat16* __restrict__ logits, long long ld, const long long* __restrict__ targets,
                               const unsigned char* __restrict__ row_mask, const float* __restrict__ lse_in,
-                              const float* __restrict__ scalars, float upstream, int V) {
+                              const float* __restrict__ scalars, float upstream, int V, int unmasked_rows_zero) {
   const long long row = blockIdx.x;
   __nv_bfloat16* x = logits + row * ld;
   if (row_mask && row_mask[row] == 0) {
+    if (unmasked_rows_zero) return;  // the head GEMM's row-mask epilogue already stored the zeros
     for (int c = threadIdx.x; c < V / 8; c += blockDim.x) reinterpret_cast<uint4*>(x)[c] = make_uint4(0, 0, 0, 0);
     return;
   }
@@ -287,12 +288,13 @@ extern "C" int obt_ce_fwd(const void* logits, long long ld, const long long* tar
 
 extern "C" int obt_ce_bwd(void* logits, long long ld, const long long* targets, const unsigned char* row_mask,
                           const float* lse, const float* scalars, float upstream, long long M, int V,
-                          cudaStream_t stream) {
+                          int unmasked_rows_zero, cudaStream_t stream) {
   OBT_REQUIRE(logits && targets && lse && scalars, "obt_ce_bwd: null pointer");
   OBT_REQUIRE(V % 8 == 0 && ld % 8 == 0, "obt_ce_bwd: V=%d ld=%lld must be multiples of 8", V, ld);
   OBT_REQUIRE(M > 0 && M < (1ll << 31), "obt_ce_bwd: bad M=%lld", M);
   ce_bwd_kernel<<<static_cast<unsigned>(M), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(logits), ld, targets,
-                                                             row_mask, lse, scalars, upstream, V);
+                                                             row_mask, lse, scalars, upstream, V,
+                                                             unmasked_rows_zero);
   return check_launch("ce_bwd");
 }
 

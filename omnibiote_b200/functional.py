@@ -218,9 +218,12 @@ class HeadLossFunction(torch.autograd.Function):
     def forward(ctx, x, gamma, weight, div, targets, loss_mask, n_acc):
         emb, z, mean, rstd = ops.layernorm_fwd(x, gamma, readout_div=div)
         del emb
-        logits = ops.gemm(z, weight)
-        scalars, lse, tok, row_mask, tgt = ops.ce_fwd(logits, targets, loss_mask, n_acc)
-        ops.ce_bwd_(logits, tgt, row_mask, lse, scalars, 1.0)
+        # the full [M, V] head GEMM; rows outside the loss mask are stored as the zeros d loss / d logits needs there
+        # (nothing ever reads their logits), so the CE kernels only touch the masked rows
+        row_mask = loss_mask.reshape(-1).to(torch.uint8).contiguous()
+        logits = ops.gemm(z, weight, epilogue=ops.EPI_ROWMASK, aux_in=row_mask)
+        scalars, lse, tok, row_mask, tgt = ops.ce_fwd(logits, targets, row_mask, n_acc)
+        ops.ce_bwd_(logits, tgt, row_mask, lse, scalars, 1.0, unmasked_rows_zero=True)
         ctx.save_for_backward(x, gamma, weight, mean, rstd, z, logits)
         ctx.div = div
         ctx.params = (gamma, weight)

@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 
-EPI_PLAIN, EPI_RESID, EPI_GELU, EPI_GELU_BWD, EPI_RESID_DROPOUT, EPI_ROPE = 0, 1, 2, 3, 5, 7
+EPI_PLAIN, EPI_RESID, EPI_GELU, EPI_GELU_BWD, EPI_RESID_DROPOUT, EPI_ROPE, EPI_ROWMASK = 0, 1, 2, 3, 5, 7, 8
 
 # gelu_mode 0: one rounding (TorchScript-fused execution on CUDA); 1: a bf16 rounding per primitive (eager CPU run of
 # the same expression, which is what the CPU oracle does). See SURVEY Appendix A.2.
@@ -92,7 +92,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a
     if tuple(out.shape) != (M, N):
         raise RuntimeError(f"omnibiote_b200: gemm D shape {tuple(out.shape)} != {(M, N)}")
     ld_ai = ld_ao = 0
-    if aux_in is not None:
+    if epilogue == EPI_ROWMASK:
+        if aux_in is None or aux_in.dtype != torch.uint8 or aux_in.numel() != M or not aux_in.is_contiguous():
+            raise RuntimeError("omnibiote_b200: EPI_ROWMASK needs aux_in = contiguous uint8 row mask [M]")
+    elif aux_in is not None:
         aux_in, ld_ai = _mat(aux_in, "gemm aux_in")
     if aux_out is not None:
         aux_out, ld_ao = _mat(aux_out, "gemm aux_out")
@@ -414,11 +417,12 @@ def ce_fwd(logits: torch.Tensor, targets: torch.Tensor, row_mask: torch.Tensor |
     return scalars, lse, tok, row_mask, targets
 
 
-def ce_bwd_(logits, targets, row_mask, lse, scalars, upstream: float = 1.0):
+def ce_bwd_(logits, targets, row_mask, lse, scalars, upstream: float = 1.0, unmasked_rows_zero: bool = False):
     logits, ld = _mat(logits, "logits")
     M, V = logits.shape
     rc = _lib.load().obt_ce_bwd(logits.data_ptr(), ld, targets.data_ptr(), _ptr(row_mask), lse.data_ptr(),
-                                scalars.data_ptr(), float(upstream), M, V, _stream())
+                                scalars.data_ptr(), float(upstream), M, V, int(unmasked_rows_zero and row_mask is not None),
+                                _stream())
     _lib.check(rc, "obt_ce_bwd")
     return logits
 

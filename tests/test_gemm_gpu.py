@@ -111,6 +111,24 @@ def test_gemm_epilogues(cg):
         lib.obt_gemm_set_cta_group(0)
 
 
+@pytest.mark.parametrize("cg", [1, 2, 3])
+def test_gemm_rowmask_epilogue(cg):
+    """Epilogue 8 (MLM head): rows outside the uint8 mask are stored as exact zeros, the others as rb(acc)."""
+    lib, ops = _ops()
+    lib.obt_gemm_set_cta_group(cg)
+    try:
+        M, N, K = 700, 520, 256
+        a, b, ref = _mk(M, N, K, False, False, seed=11)
+        g = torch.Generator(device="cuda").manual_seed(1)
+        mask = (torch.rand(M, generator=g, device="cuda") < 0.15).to(torch.uint8)
+        out = ops.gemm(a, b, epilogue=ops.EPI_ROWMASK, aux_in=mask, allow_splitk=False)
+        plain = ops.gemm(a, b, allow_splitk=False)
+        assert torch.equal(out[mask.bool()], plain[mask.bool()])
+        assert float(out[~mask.bool()].abs().max()) == 0.0
+    finally:
+        lib.obt_gemm_set_cta_group(0)
+
+
 @pytest.mark.parametrize("cg", [1, 2, 3])  # 1 CTA / cta_group::2 pair / 2-CTA cluster with multicast B
 def test_gemm_splitk_wgrad_shape(cg):
     lib, ops = _ops()
