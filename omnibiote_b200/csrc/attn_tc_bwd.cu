@@ -310,13 +310,24 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
       __syncwarp();
       if (lane == 0) mbar_arrive(&ds_full[bsel]);
     }
-    // dQ epilogue: this thread stores columns [64*hh, 64*hh+64) of its row
+    // dQ epilogue: this thread stores columns [64*hh, 64*hh+64) of its row; its rotary table entries are fetched
+    // before the wait for the last MMA
+    const bool do_rope = row_ok && p.rope_cos != nullptr;
+    float4 rcs[8], rsn[8];
+    if (do_rope) {
+      const long long toff = static_cast<long long>(i) * (ATT_D / 2) + hh * 32;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        rcs[g] = reinterpret_cast<const float4*>(p.rope_cos + toff)[g];
+        rsn[g] = p.rope_sin ? reinterpret_cast<const float4*>(p.rope_sin + toff)[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     mbar_wait(dq_done, 0);
     tc_fence_after();
     __nv_bfloat16* drow = p.dq + (static_cast<long long>(row0) + i) * p.ldd + h * ATT_D;
     const float oscale = row_scale * inv_keep;
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {  // unrolled: the prefetched table entries stay in registers
       const int c = hh * 2 + cc;
       uint32_t o[32];
       __syncwarp();
@@ -326,11 +337,10 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
         float f[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(o[e]) * oscale;
-        if (p.rope_cos != nullptr) {  // adjoint of the rotary embedding: dqkv is the gradient of c_attn's raw output
+        if (do_rope) {  // adjoint of the rotary embedding: dqkv is the gradient of c_attn's raw output
 #pragma unroll
           for (int e = 0; e < 32; ++e) f[e] = rb(f[e]);
-          const long long toff = static_cast<long long>(i) * (ATT_D / 2) + c * 16;
-          rope_adjoint32(f, p.rope_cos + toff, p.rope_sin ? p.rope_sin + toff : nullptr);
+          rope_adjoint32(f, &rcs[cc * 4], &rsn[cc * 4], p.rope_sin != nullptr);
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g)
@@ -590,11 +600,15 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       return it;
     };
 
+    // two sub-tiles of look-ahead: the keep words come from HBM (written a whole forward pass earlier) and one
+    // sub-tile of math (~1 us) did not cover that latency (11 % of the stall samples sat on the first use)
     int n = 0;
     int it = next_relevant(-1);
-    QParams cur = {};
+    int nx = it < nq ? next_relevant(it) : nq;
+    QParams cur = {}, zn = {};
     if (it < nq) {
       cur = load_params(it);
+      if (nx < nq) zn = load_params(nx);
       finish_params(cur, it);
       store_params(0, cur);
     }
@@ -602,9 +616,9 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     while (it < nq) {
       const int st = n & 1;
       const int i0 = it * 64 + hh * 32;
-      const int nx = next_relevant(it);
-      QParams zn = {};
-      if (nx < nq) zn = load_params(nx);  // in flight during the math below
+      const int nx2 = nx < nq ? next_relevant(nx) : nq;
+      QParams zn2 = {};
+      if (nx2 < nq) zn2 = load_params(nx2);  // in flight during the math of this AND the next sub-tile
       const uint8_t* base = wpar + st * ATT_WPAR_BYTES;
       const float4* nd4 = reinterpret_cast<const float4*>(base);            // two queries per float4
       const int2* c_lh = reinterpret_cast<const int2*>(base + 256);
@@ -735,20 +749,33 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         store_params(st ^ 1, zn);
       }
       cur = zn;
+      zn = zn2;
       __syncwarp();
       it = nx;
+      nx = nx2;
       ++n;
     }
     // epilogue: hh = 0 stores dV (TMEM columns 256..383) / (1-p), hh = 1 stores dK (384..511) * scale / (1-p)
     __nv_bfloat16* dvrow = p.dv + (static_cast<long long>(row0) + j) * p.ldd + h * ATT_D;
     __nv_bfloat16* dkrow = p.dk + (static_cast<long long>(row0) + j) * p.ldd + h * ATT_D;
     const float oscale = hh == 0 ? inv_keep : inv_keep * p.scale;
+    // rotary table row of this key (dK only), fetched before the wait for the last MMAs
+    const bool do_rope = hh == 1 && key_ok && p.rope_cos != nullptr;
+    float4 rcs[16], rsn[16];
+    if (do_rope) {
+      const long long toff = static_cast<long long>(j) * (ATT_D / 2);
+#pragma unroll
+      for (int g = 0; g < 16; ++g) {
+        rcs[g] = reinterpret_cast<const float4*>(p.rope_cos + toff)[g];
+        rsn[g] = p.rope_sin ? reinterpret_cast<const float4*>(p.rope_sin + toff)[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     if (n > 0) {
       mbar_wait(grads_done, 0);
       tc_fence_after();
     }
-#pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {  // unrolled: the prefetched table entries stay in registers
       const int c = hh * 4 + cc;
       uint32_t o[32];
       __syncwarp();
@@ -764,11 +791,10 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         float f[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(o[e]) * oscale;
-        if (c >= 4 && p.rope_cos != nullptr) {  // dK: adjoint of the rotary embedding at key position j
+        if (do_rope) {  // dK: adjoint of the rotary embedding at key position j
 #pragma unroll
           for (int e = 0; e < 32; ++e) f[e] = rb(f[e]);
-          const long long toff = static_cast<long long>(j) * (ATT_D / 2) + (c & 3) * 16;
-          rope_adjoint32(f, p.rope_cos + toff, p.rope_sin ? p.rope_sin + toff : nullptr);
+          rope_adjoint32(f, &rcs[cc * 4], &rsn[cc * 4], p.rope_sin != nullptr);
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g)

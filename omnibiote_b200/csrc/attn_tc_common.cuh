@@ -38,20 +38,19 @@ struct AttnTcParams {
   const float* rope_sin;
 };
 
-// adjoint rotary on 32 consecutive d-columns (16 pairs) of one gradient row, values already scaled (fp32)
-__device__ __forceinline__ void rope_adjoint32(float (&f)[32], const float* __restrict__ ct, const float* __restrict__ st) {
+// adjoint rotary on 32 consecutive d-columns (16 pairs) of one gradient row, values already scaled (fp32); cs / sn:
+// the 16 table entries of those pairs (4 x float4), already in registers
+__device__ __forceinline__ void rope_adjoint32(float (&f)[32], const float4* cs, const float4* sn, bool has_sin) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const float4 c4 = reinterpret_cast<const float4*>(ct)[g];
-    const float c[4] = {c4.x, c4.y, c4.z, c4.w};
-    if (st != nullptr) {
-      const float4 s4 = reinterpret_cast<const float4*>(st)[g];
-      const float sn[4] = {s4.x, s4.y, s4.z, s4.w};
+    const float c[4] = {cs[g].x, cs[g].y, cs[g].z, cs[g].w};
+    if (has_sin) {
+      const float s4[4] = {sn[g].x, sn[g].y, sn[g].z, sn[g].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float a = f[g * 8 + 2 * j], b = f[g * 8 + 2 * j + 1];
-        f[g * 8 + 2 * j] = a * c[j] + b * sn[j];
-        f[g * 8 + 2 * j + 1] = b * c[j] - a * sn[j];
+        f[g * 8 + 2 * j] = a * c[j] + b * s4[j];
+        f[g * 8 + 2 * j + 1] = b * c[j] - a * s4[j];
       }
     } else {
 #pragma unroll
@@ -75,21 +74,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-
-// Issue the 8 UMMA (k = 16 each) of one 128x128x128 product.
-//   a_addr: K-major A tile (two 64-wide sub-tiles); b_addr: B tile, K-major (kBMN = false) or MN-major (kBMN = true:
-//   the same TMA-written bytes read as [K rows][128 B of N], second 64 columns of N 16 KB further).
-template <bool kBMN>
-__device__ __forceinline__ void issue_128x128x128(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, bool accumulate) {
-  constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, kBMN);
-#pragma unroll
-  for (int kk = 0; kk < 8; ++kk) {
-    const uint64_t a_desc = make_smem_desc_sw128(a_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024);
-    const uint64_t b_desc = kBMN ? make_smem_desc_sw128(b_addr + kk * 2048, 16384, 1024)
-                                 : make_smem_desc_sw128(b_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024);
-    umma_bf16_ss<1>(d_tmem, a_desc, b_desc, idesc, (accumulate || kk > 0) ? 1u : 0u);
-  }
 }
 
 // D[128 x 64] = A[128 x 128(d)] * B[64 x 128(d)]^T, both K-major; a tile = two 64-column sub-tiles `a_sub` /
