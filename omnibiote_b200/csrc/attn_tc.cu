@@ -205,15 +205,18 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     if (kDrop && row_ok) keep_row = p.keep + ((static_cast<long long>(b) * p.H + h) * T + i) * p.nw;
     float m_ref = -INFINITY, l_run = 0.f;  // reference max (log2 domain) and exp-sum relative to it
 
+    // keep words one tile ahead (they come from HBM: the mask generator ran before the c_attn GEMM)
+    auto load_kw = [&](int jj, int u) -> uint32_t {
+      const int w = (((jb + jj) * FWD_BN) >> 5) + u;
+      return (kDrop && keep_row != nullptr && jj < n_tiles && w < p.nw) ? keep_row[w] : 0xffffffffu;
+    };
+    uint32_t kw0_next = load_kw(0, 0), kw1_next = load_kw(0, 1);
     for (int jj = 0; jj < n_tiles; ++jj) {
       const int st = jj & 1;
       const int j0 = (jb + jj) * FWD_BN;
-      uint32_t kw0 = 0xffffffffu, kw1 = 0xffffffffu;
-      if (kDrop && keep_row != nullptr) {  // issued before the wait: the latency hides behind the MMA
-        const int w = j0 >> 5;
-        if (w < p.nw) kw0 = keep_row[w];
-        if (w + 1 < p.nw) kw1 = keep_row[w + 1];
-      }
+      const uint32_t kw0 = kw0_next, kw1 = kw1_next;
+      kw0_next = load_kw(jj + 1, 0);
+      kw1_next = load_kw(jj + 1, 1);
       mbar_wait(&s_full[st], (jj >> 1) & 1);
       tc_fence_after();
       const uint32_t s_addr = lane_addr + st * 64;

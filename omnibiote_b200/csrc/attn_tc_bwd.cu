@@ -61,7 +61,7 @@ struct AttnDqSmem {
 };
 
 template <bool kDrop>
-__global__ void __launch_bounds__(ATT_THREADS_BWD, 1)
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16* __restrict__ qkv, long long ld,
                   const __nv_bfloat16* __restrict__ dy, long long lddy, const AttnTcParams p, int C) {
   // 1024-byte alignment (128B-swizzle atoms) is requested from the toolchain, so every smem address below is a
@@ -86,6 +86,23 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
   const int t0 = blockIdx.x * ATT_BM;
   const int h = blockIdx.y, b = blockIdx.z;
   const int T = p.T;
+
+  // Compute threads (warps 4..11: two per query row, d columns [64*hh, +64)) issue the global loads of their Q and dO
+  // half-rows FIRST: ~1 us of latency that now overlaps the barrier / TMEM set-up and the interval scan instead of
+  // heading the critical path (17 % of the stall samples of v6, profiles/r01_attn_v8_dq.source.txt).
+  uint4 qv[8], dov[8];
+  {
+    const int r_ = (warp & 3) * 32 + lane, hh_ = (warp - ATT_BWD_FIRST_COMPUTE_WARP) >> 2;
+    const bool ok_ = warp >= ATT_BWD_FIRST_COMPUTE_WARP && t0 + r_ < T;
+    const long long row_ = static_cast<long long>(b) * T + t0 + r_;
+    const uint4* src = reinterpret_cast<const uint4*>(qkv + row_ * ld + h * ATT_D + hh_ * 64);
+    const uint4* src2 = reinterpret_cast<const uint4*>(dy + row_ * lddy + h * ATT_D + hh_ * 64);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      qv[g] = ok_ ? src[g] : make_uint4(0, 0, 0, 0);
+      dov[g] = ok_ ? src2[g] : make_uint4(0, 0, 0, 0);
+    }
+  }
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -123,18 +140,27 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
   // shuffled from lane 0 so that the compiler knows the value is warp-uniform: tcgen05 operands then go through
   // uniform registers directly instead of a per-lane R2UR waterfall loop around every MMA
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tmem_slot), 0);
-  int jb = 0, je = (T + ATT_BN - 1) / ATT_BN;
-  if (p.row_lo != nullptr && s_range[2] == 0 && s_range[1] > s_range[0]) {
-    jb = s_range[0] / ATT_BN;
-    je = (s_range[1] + ATT_BN - 1) / ATT_BN;
-  }
-  const int n_tiles = je - jb;   // 128-key tiles
-  const int n_sub = 2 * n_tiles;  // 64-key sub-tiles
+  // first / one-past-last 128-key tile; evaluated inside each role branch (values live across the role split would
+  // be spilled for the register-poor branch and reloaded in the compute loop)
+  auto tile_range = [&](int& jb_out, int& je_out) {
+    jb_out = 0;
+    je_out = (T + ATT_BN - 1) / ATT_BN;
+    if (p.row_lo != nullptr && s_range[2] == 0 && s_range[1] > s_range[0]) {
+      jb_out = s_range[0] / ATT_BN;
+      je_out = (s_range[1] + ATT_BN - 1) / ATT_BN;
+    }
+  };
   const int row0 = b * T;
   const int kcol = C + h * ATT_D, vcol = 2 * C + h * ATT_D;
   constexpr uint32_t TM_DQ = 256, TM_Q = 384, TM_DO = 448;
 
-  if (warp == 0) {
+  if (warp < ATT_BWD_FIRST_COMPUTE_WARP) {
+   reg_dealloc<56>();
+   int jb, je;
+   tile_range(jb, je);
+   const int n_tiles = je - jb;   // 128-key tiles
+   const int n_sub = 2 * n_tiles;  // 64-key sub-tiles
+   if (warp == 0) {
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
@@ -191,29 +217,30 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
       }
       __syncwarp();
     }
+   }
   } else {
+    reg_alloc<224>();
+    int jb, je;
+    tile_range(jb, je);
+    const int n_sub = 2 * (je - jb);  // 64-key sub-tiles
     const int q = warp & 3;
-    const int hh = (warp - 2) >> 2;  // two threads per query row: columns [32*hh, +32) of every 64-key sub-tile
+    const int hh = (warp - ATT_BWD_FIRST_COMPUTE_WARP) >> 2;  // two threads per query row: columns [32*hh, +32)
     const int r = q * 32 + lane;
     const int i = t0 + r;
     const bool row_ok = i < T;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    // ---- Q and dO rows -> TMEM (this thread: d columns [64*hh, +64) = 32 packed words of each)
+    // ---- Q and dO rows (loaded at kernel entry) -> TMEM: 32 packed words of each
     {
       uint32_t w[32];
-      const uint4* src = reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(row0) + i) * ld + h * ATT_D + hh * 64);
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        const uint4 u = row_ok ? src[g] : make_uint4(0, 0, 0, 0);
-        w[g * 4 + 0] = u.x; w[g * 4 + 1] = u.y; w[g * 4 + 2] = u.z; w[g * 4 + 3] = u.w;
+        w[g * 4 + 0] = qv[g].x; w[g * 4 + 1] = qv[g].y; w[g * 4 + 2] = qv[g].z; w[g * 4 + 3] = qv[g].w;
       }
       __syncwarp();
       tmem_st_32x32(lane_addr + TM_Q + hh * 32, w);
-      const uint4* src2 = reinterpret_cast<const uint4*>(dy + (static_cast<long long>(row0) + i) * lddy + h * ATT_D + hh * 64);
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        const uint4 u = row_ok ? src2[g] : make_uint4(0, 0, 0, 0);
-        w[g * 4 + 0] = u.x; w[g * 4 + 1] = u.y; w[g * 4 + 2] = u.z; w[g * 4 + 3] = u.w;
+        w[g * 4 + 0] = dov[g].x; w[g * 4 + 1] = dov[g].y; w[g * 4 + 2] = dov[g].z; w[g * 4 + 3] = dov[g].w;
       }
       tmem_st_32x32(lane_addr + TM_DO + hh * 32, w);
       tmem_st_wait();
@@ -246,11 +273,17 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
     const uint32_t* keep_row = nullptr;
     if (kDrop && row_ok) keep_row = p.keep + (bh * T + i) * p.nw;
 
+    // keep words one sub-tile ahead (they come from HBM: written a whole forward pass earlier)
+    auto load_kw = [&](int s) -> uint32_t {
+      const int w = ((jb + (s >> 1)) * ATT_BN + (s & 1) * 64 + hh * 32) >> 5;
+      return (kDrop && keep_row != nullptr && s < n_sub && w < p.nw) ? keep_row[w] : 0xffffffffu;
+    };
+    uint32_t kw_next = load_kw(0);
     for (int s = 0; s < n_sub; ++s) {
       const int bsel = s & 1;
       const int j0 = (jb + (s >> 1)) * ATT_BN + (s & 1) * 64 + hh * 32;  // first key of this thread's 32 columns
-      uint32_t kw = 0xffffffffu;
-      if (kDrop && keep_row != nullptr && (j0 >> 5) < p.nw) kw = keep_row[j0 >> 5];
+      const uint32_t kw = kw_next;
+      kw_next = load_kw(s + 1);
       mbar_wait(&sdp_full[bsel], (s >> 1) & 1);
       tc_fence_after();
       uint32_t sv[32], dv[32];
@@ -368,12 +401,7 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
 // =============================================================================================
 constexpr uint32_t ATT_SUB_BYTES = 64 * 128 * 2;  // one [64 rows x 128] bf16 tile = two 8 KB swizzle sub-tiles
 constexpr int ATT_QDO_STAGES = 4;
-// 12 warps: warpgroup 0 = {TMA producer, MMA issuer, 2 idle}, warpgroups 1-2 = the 8 compute warps. Three warps share
-// each scheduler's 16 K registers (168 per thread at launch); v6 with 10 warps spilled in the compute loop and
-// reloaded the spills on the critical path (7 % of all stall samples, profiles/r01_attn_v7_bwd.source.txt). With the
-// roles aligned to warpgroups, warpgroup 0 returns registers (setmaxnreg.dec) and the compute warps take them.
-constexpr int ATT_DKV_THREADS = 384;
-constexpr int ATT_DKV_FIRST_COMPUTE_WARP = 4;
+
 // per warp and buffer: 32 x float2 {-(max+lsum)*log2e, delta*(1-p)} + 32 x int2 {lo,hi} + 32 x float2 {max, lsum*log2e}
 // + 32 x float live + 32 keep words + 32 visibility words (which of the warp's 32 keys each query sees)
 constexpr uint32_t ATT_WPAR_BYTES = 1152;
@@ -389,7 +417,7 @@ struct AttnDkvSmem {
 };
 
 template <bool kDrop>
-__global__ void __launch_bounds__(ATT_DKV_THREADS, 1)
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_q64,
                    const __grid_constant__ CUtensorMap tm_dy64, const AttnTcParams p, int C) {
   // 1024-byte alignment (128B-swizzle atoms) is requested from the toolchain, so every smem address below is a
@@ -480,7 +508,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   // spilled, with the reloads on the compute loop's critical path
   auto relevant = [&](int it) -> bool { return (s_rel[it >> 5] >> (it & 31)) & 1u; };
 
-  if (warp < ATT_DKV_FIRST_COMPUTE_WARP) {
+  if (warp < ATT_BWD_FIRST_COMPUTE_WARP) {
    reg_dealloc<56>();
    if (warp == 0) {
     if (lane == 0) {
@@ -538,7 +566,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   } else {
     reg_alloc<224>();
     const int q = warp & 3;
-    const int hh = (warp - ATT_DKV_FIRST_COMPUTE_WARP) >> 2;  // two threads per key row: query columns [32*hh, +32)
+    const int hh = (warp - ATT_BWD_FIRST_COMPUTE_WARP) >> 2;  // two threads per key row: query columns [32*hh, +32)
     const int r = q * 32 + lane;     // key row within the tile
     const int j = j0 + r;
     const bool key_ok = j < T;
@@ -549,7 +577,7 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const float keep_frac = kDrop ? 1.0f - p.drop_p : 1.0f;
     const float sc2 = p.scale * LOG2E;
     const uint32_t mybit = 1u << keep_bit_pos(lane);  // this key's bit inside the keep word of its 32-key group
-    uint8_t* wpar = sPar + (warp - ATT_DKV_FIRST_COMPUTE_WARP) * 2 * ATT_WPAR_BYTES;
+    uint8_t* wpar = sPar + (warp - ATT_BWD_FIRST_COMPUTE_WARP) * 2 * ATT_WPAR_BYTES;
     // Per-query parameters of THIS warp's 32 query columns (lane = query), software-pipelined: the global loads for
     // the next relevant sub-tile are issued before the math of the current one and staged in the warp's other smem
     // buffer afterwards; the math reads them back as warp-wide broadcasts.
@@ -883,16 +911,16 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
   }
   dim3 grid((T + ATT_BM - 1) / ATT_BM, H, B);
   if (drop_p > 0.f)
-    attn_tc_dq_kernel<true><<<grid, ATT_THREADS_BWD, AttnDqSmem::BYTES, stream>>>(
+    attn_tc_dq_kernel<true><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(
         tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
   else
-    attn_tc_dq_kernel<false><<<grid, ATT_THREADS_BWD, AttnDqSmem::BYTES, stream>>>(
+    attn_tc_dq_kernel<false><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(
         tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
   rc = check_launch("attn_tc_dq");
   if (rc) return rc;
   if (drop_p > 0.f)
-    attn_tc_dkv_kernel<true><<<grid, ATT_DKV_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
+    attn_tc_dkv_kernel<true><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
   else
-    attn_tc_dkv_kernel<false><<<grid, ATT_DKV_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
+    attn_tc_dkv_kernel<false><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
   return check_launch("attn_tc_dkv");
 }

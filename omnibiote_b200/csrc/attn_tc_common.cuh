@@ -154,6 +154,11 @@ __device__ __forceinline__ uint32_t interval_bits32(int lo, int hi, int base) {
 __device__ __forceinline__ void compute_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 constexpr int ATT_COMPUTE_WARPS = 8;
-constexpr int ATT_THREADS_BWD = 64 + 32 * ATT_COMPUTE_WARPS;
+// Backward kernels: 12 warps. Warpgroup 0 = {TMA producer, MMA issuer, 2 idle}, warpgroups 1-2 = the 8 compute warps.
+// Three warps share each scheduler's 16 K registers (168 per thread at launch); with the roles aligned to warpgroups,
+// warpgroup 0 returns registers (setmaxnreg.dec) and the compute warps take them (224 each): the 10-warp layout
+// spilled in the compute loops and reloaded the spills on the critical path (profiles/r01_attn_v7_bwd.source.txt).
+constexpr int ATT_BWD_THREADS = 384;
+constexpr int ATT_BWD_FIRST_COMPUTE_WARP = 4;
 
 }  // namespace obt
