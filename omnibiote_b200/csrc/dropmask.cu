@@ -1,16 +1,19 @@
 // Generator of the attention-dropout keep mask (see dropmask.cuh): the dropout of
 // F.scaled_dot_product_attention(..., dropout_p) (training/model.py:118,134) as a bit matrix keep[B,H,T,ceil(T/32)].
 //
-// One thread draws whole 32-key words: sixteen 32-bit hash words r_15..r_0 are read as the bit planes of thirty-two
-// 16-bit uniforms u_e, and the comparison u_e < round(p * 2^16) is evaluated for all 32 keys at once with bitwise
-// logic (a bit-serial magnitude comparator, MSB first): ~4 integer instructions per element at full issue rate,
-// none of them inside the attention kernels. The stream is counter based: (seed, offset, flat word index).
+// One thread draws whole 32-key words: twelve 32-bit hash words r_11..r_0 are read as the bit planes of thirty-two
+// 12-bit uniforms u_e, and the comparison u_e < round(p * 2^12) is evaluated for all 32 keys at once with bitwise
+// logic (a bit-serial magnitude comparator, MSB first): ~3.5 integer instructions per element at full issue rate,
+// none of them inside the attention kernels. The drop probability is p rounded to 1/4096 (0.1 -> 0.10010); the
+// 1/(1-p) scaling uses the caller's p. The stream is counter based: (seed, offset, flat word index).
 #include "common.cuh"
 #include "dropmask.cuh"
 
 namespace obt {
 
-__device__ __forceinline__ uint32_t keep_word_draw(uint32_t k0, uint32_t k1, unsigned long long widx, uint32_t thr16) {
+constexpr int KEEP_PLANES = 12;  // bits of the per-element uniform
+
+__device__ __forceinline__ uint32_t keep_word_draw(uint32_t k0, uint32_t k1, unsigned long long widx, uint32_t thr) {
   const uint32_t c0 = static_cast<uint32_t>(widx), c1 = static_cast<uint32_t>(widx >> 32);
   // two keyed 32-bit murmur3 finalisers of the word index
   uint32_t a = (c0 * 0x9E3779B1u) ^ k0 ^ (c1 * 0x85EBCA77u);
@@ -19,30 +22,30 @@ __device__ __forceinline__ uint32_t keep_word_draw(uint32_t k0, uint32_t k1, uns
   b ^= b >> 16; b *= 0x7FEB352Du; b ^= b >> 15; b *= 0x846CA68Bu; b ^= b >> 16;
   uint32_t lt = 0u, eq = 0xffffffffu;
 #pragma unroll
-  for (int k = 15; k >= 0; --k) {
+  for (int k = KEEP_PLANES - 1; k >= 0; --k) {
     // bit plane k: a two-multiply mix of (a, b, k)
     uint32_t x = a * 0x2C1B3C6Du + static_cast<uint32_t>(k + 1) * 0x9E3779B9u;
     x ^= x >> 15;
     x = x * 0x297A2D39u + b;
     x ^= x >> 13;
-    if ((thr16 >> k) & 1u) {  // uniform branch
+    if ((thr >> k) & 1u) {  // uniform branch
       lt |= eq & ~x;
       eq &= x;
     } else {
       eq &= ~x;
     }
   }
-  return ~lt;  // keep <=> u >= thr16
+  return ~lt;  // keep <=> u >= thr
 }
 
 // grid.x covers the B*H*T*nw words, 8 consecutive words (256 keys of one query row) per thread
-__global__ void attn_keep_mask_kernel(uint32_t* __restrict__ keep, long long n_words, uint32_t thr16, uint32_t k0,
+__global__ void attn_keep_mask_kernel(uint32_t* __restrict__ keep, long long n_words, uint32_t thr, uint32_t k0,
                                       uint32_t k1) {
   const long long w0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (w0 >= n_words) return;
   uint32_t out[8];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) out[u] = keep_word_draw(k0, k1, static_cast<unsigned long long>(w0 + u), thr16);
+  for (int u = 0; u < 8; ++u) out[u] = keep_word_draw(k0, k1, static_cast<unsigned long long>(w0 + u), thr);
   if (w0 + 8 <= n_words && (reinterpret_cast<uintptr_t>(keep + w0) & 15) == 0) {
     reinterpret_cast<uint4*>(keep + w0)[0] = make_uint4(out[0], out[1], out[2], out[3]);
     reinterpret_cast<uint4*>(keep + w0)[1] = make_uint4(out[4], out[5], out[6], out[7]);
@@ -63,12 +66,12 @@ extern "C" int obt_attn_keep_mask(unsigned int* keep, int B, int H, int T, float
   OBT_REQUIRE(B > 0 && H > 0 && T > 0, "obt_attn_keep_mask: empty problem");
   OBT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "obt_attn_keep_mask: dropout p=%f", drop_p);
   const long long n_words = static_cast<long long>(B) * H * T * keep_words(T);
-  uint32_t thr16 = static_cast<uint32_t>(drop_p * 65536.0f + 0.5f);
-  if (thr16 > 65535u) thr16 = 65535u;
+  uint32_t thr = static_cast<uint32_t>(drop_p * static_cast<float>(1 << KEEP_PLANES) + 0.5f);
+  if (thr > (1u << KEEP_PLANES) - 1u) thr = (1u << KEEP_PLANES) - 1u;
   const unsigned long long key = seed ^ (offset * 0xD1B54A32D192ED03ull);
   const int threads = 256;
   const long long per_block = static_cast<long long>(threads) * 8;
   attn_keep_mask_kernel<<<static_cast<unsigned>((n_words + per_block - 1) / per_block), threads, 0, stream>>>(
-      keep, n_words, thr16, static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32));
+      keep, n_words, thr, static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32));
   return check_launch("attn_keep_mask");
 }
