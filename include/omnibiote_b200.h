@@ -39,6 +39,8 @@ void obt_clear_descriptor_cache(void);
  *           2 aux_out = U = rb(acc); D = rb(gelu(U))   fused_gelu (model.py:23-25)
  *           3 D = rb(rb(acc) * gelu'(aux_in))          backward of fused_gelu, aux_in = U
  *           5 D = rb(aux_in + dropout(rb(acc)))        resid_dropout + residual (model.py:151,167,179-180)
+ *           9 aux_out = rb(gelu'(U)), D = rb(gelu(U)) with U = rb(acc): forward of fused_gelu that saves the DERIVATIVE
+ *          10 D = rb(rb(acc) * aux_in): its backward (aux_in = the saved derivative); 9 + 10 replace 2 + 3 in the block
  *           8 D = aux_in[row] ? rb(acc) : 0 with aux_in a uint8 row mask [M]: MLM head whose unmasked rows are never
  *             read (zero loss weight and gradient, train_encoder.py:301-305); pairs with obt_ce_bwd(unmasked_rows_zero)
  *           7 D = rb(rotary(rb(acc))) on columns < rope_cols: apply_rotary_emb (model.py:39-50,108) fused into

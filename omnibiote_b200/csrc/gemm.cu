@@ -369,8 +369,7 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   OBT_REQUIRE(A && B && D, "obt_gemm_bf16: null operand");
   OBT_REQUIRE(M > 0 && N > 0 && K > 0, "obt_gemm_bf16: empty problem M=%lld N=%lld K=%lld", M, N, K);
   OBT_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "obt_gemm_bf16: dims exceed int32");
-  OBT_REQUIRE(((epilogue >= EPI_PLAIN && epilogue <= EPI_RESID_DROPOUT) || epilogue == EPI_ROPE ||
-               epilogue == EPI_ROWMASK) &&
+  OBT_REQUIRE(((epilogue >= EPI_PLAIN && epilogue <= EPI_RESID_DROPOUT) || (epilogue >= EPI_ROPE && epilogue <= EPI_MUL)) &&
                   epilogue != EPI_PARTIAL,
               "obt_gemm_bf16: bad epilogue %d", epilogue);
   if (epilogue == EPI_ROPE)
@@ -378,9 +377,11 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
                     (reinterpret_cast<uintptr_t>(rope_cos) & 15) == 0 && (reinterpret_cast<uintptr_t>(rope_sin) & 15) == 0,
                 "obt_gemm_bf16: rotary epilogue needs 16-byte aligned fp32 tables, head_dim %% 8 == 0 (got %d), "
                 "rope_cols %% 8 == 0 (got %d)", rope_head_dim, rope_cols);
-  if (epilogue == EPI_RESID || epilogue == EPI_GELU_BWD || epilogue == EPI_RESID_DROPOUT || epilogue == EPI_ROWMASK)
+  if (epilogue == EPI_RESID || epilogue == EPI_GELU_BWD || epilogue == EPI_RESID_DROPOUT || epilogue == EPI_ROWMASK ||
+      epilogue == EPI_MUL)
     OBT_REQUIRE(aux_in != nullptr, "obt_gemm_bf16: epilogue %d needs aux_in", epilogue);
-  if (epilogue == EPI_GELU) OBT_REQUIRE(aux_out != nullptr, "obt_gemm_bf16: GELU epilogue needs aux_out");
+  if (epilogue == EPI_GELU || epilogue == EPI_GELU_DG)
+    OBT_REQUIRE(aux_out != nullptr, "obt_gemm_bf16: GELU epilogue needs aux_out");
 
   int cg = g_force_cta_group;
   // auto: one CTA per SM with 128x256 tiles measured 1.17-1.40 PFLOP/s on the block/head shapes (86-95 % of cuBLAS);

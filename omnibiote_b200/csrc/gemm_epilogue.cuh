@@ -25,6 +25,10 @@ enum : int {
   EPI_GELU_EAGER = 6,     // internal: EPI_GELU with one bf16 rounding per primitive (gelu_mode = 1)
   EPI_ROPE = 7,           // D = rb(rotary(rb(acc))) on columns < rope_cols (q | k of the fused c_attn output):
                           // apply_rotary_emb (model.py:39-50,108) fused into the c_attn GEMM
+  EPI_GELU_DG = 9,        // aux_out = rb(gelu'(rb(acc))); D = rb(gelu(rb(acc))): the forward stores the activation's
+                          // DERIVATIVE instead of the pre-activation (one erf evaluation serves both), so that
+  EPI_MUL = 10,           // D = rb(rb(acc) * aux_in) is all the backward's epilogue has to do (the GELU' epilogue
+                          // was the slowest GEMM of the step: 291 us vs 185 us for the same FLOPs)
   EPI_ROWMASK = 8,        // D = row_mask[row] ? rb(acc) : 0 with aux_in = uint8 [M]: the MLM head's logits of rows
                           // outside the loss mask are never read (their loss weight and gradient are exactly zero,
                           // train_encoder.py:301-305), so the zeros d loss / d logits needs there are stored right away
@@ -88,6 +92,15 @@ __device__ __noinline__ float gelu_eager(float x) {
   return a * d;  // caller rounds
 }
 
+// gelu(x) and gelu'(x) from ONE erf / exp evaluation
+__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
+  const float inv = 1.0f / 1.41421f;
+  float cdf2, e;
+  one_plus_erf(x * inv, cdf2, e);
+  g = (0.5f * x) * cdf2;
+  dg = fmaf(x * (0.5f * 1.1283791670955126f * inv), e, 0.5f * cdf2);
+}
+
 __device__ __forceinline__ float gelu_grad_ref(float x) {
   const float inv = 1.0f / 1.41421f;
   float cdf2, e;
@@ -125,8 +138,9 @@ __device__ __forceinline__ void rope8(float (&v)[8], const float4& cs, const flo
 
 template <int EPI>
 struct EpiTraits {
-  static constexpr bool kAuxIn = (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_RESID_DROPOUT);
-  static constexpr bool kAuxOut = (EPI == EPI_GELU || EPI == EPI_GELU_EAGER);
+  static constexpr bool kAuxIn =
+      (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_RESID_DROPOUT || EPI == EPI_MUL);
+  static constexpr bool kAuxOut = (EPI == EPI_GELU || EPI == EPI_GELU_EAGER || EPI == EPI_GELU_DG);
 };
 
 // v: rb(acc) for 8 consecutive columns; a: aux_in values (when the epilogue has one). Returns D in v, U in u.
@@ -160,6 +174,12 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, float (&v)[8]
       u[e] = v[e];
       v[e] = gelu_fused(v[e]);
     }
+  } else if constexpr (EPI == EPI_GELU_DG) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gelu_and_grad(v[e], v[e], u[e]);
+  } else if constexpr (EPI == EPI_MUL) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = v[e] * a[e];
   } else if constexpr (EPI == EPI_GELU_EAGER) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -361,6 +381,8 @@ __device__ __forceinline__ void epilogue_warp_tile(const GemmParams& p, uint32_t
       break;
     case EPI_ROPE: epilogue_chunks<EPI_ROPE>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
     case EPI_ROWMASK: epilogue_chunks<EPI_ROWMASK>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
+    case EPI_GELU_DG: epilogue_chunks<EPI_GELU_DG>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
+    case EPI_MUL: epilogue_chunks<EPI_MUL>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
     default: epilogue_chunks<EPI_GELU_EAGER>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
   }
 }

@@ -114,8 +114,11 @@ class BlockFunction(torch.autograd.Function):
         else:
             x1 = ops.gemm(y, w_o, epilogue=ops.EPI_RESID, aux_in=x)
         h2, _, mean2, rstd2 = ops.layernorm_fwd(x1, g2)
+        # u = gelu'(c_fc output), not the pre-activation: one erf evaluation in the forward epilogue serves both, and the
+        # backward's epilogue becomes a single multiply (GELU_MODE 1 keeps the eager-rounding pair 2 + 3)
         u = torch.empty((M, w_fc.shape[0]), dtype=torch.bfloat16, device=dev)
-        g = ops.gemm(h2, w_fc, epilogue=ops.EPI_GELU, aux_out=u)
+        fused_dg = ops.GELU_MODE == 0
+        g = ops.gemm(h2, w_fc, epilogue=ops.EPI_GELU_DG if fused_dg else ops.EPI_GELU, aux_out=u)
         if p > 0.0:
             x2 = ops.gemm(g, w_pr, epilogue=ops.EPI_RESID_DROPOUT, aux_in=x1, drop_p=p, seed=seeds[2][0], offset=seeds[2][1])
         else:
@@ -126,6 +129,7 @@ class BlockFunction(torch.autograd.Function):
         ctx.mask = mask
         ctx.keep = keep
         ctx.meta = (B, T, H, d, p, seeds, scale)
+        ctx.fused_dg = fused_dg
         ctx.params = (g1, w_qkv, w_o, g2, w_fc, w_pr)
         return x2
 
@@ -142,7 +146,7 @@ class BlockFunction(torch.autograd.Function):
         # ---- MLP branch: x2 = x1 + dropout(g @ Wpr^T)
         d_dd = ops.dropout(dx2, p, *seeds[2]) if p > 0.0 else dx2
         dw_pr = _wgrad(d_dd, g, ppr)
-        du = ops.gemm(d_dd, w_pr, b_mn=True, epilogue=ops.EPI_GELU_BWD, aux_in=u)
+        du = ops.gemm(d_dd, w_pr, b_mn=True, epilogue=ops.EPI_MUL if ctx.fused_dg else ops.EPI_GELU_BWD, aux_in=u)
         dw_fc = _wgrad(du, h2, pfc)
         dh2 = ops.gemm(du, w_fc, b_mn=True)
         acc2 = direct and pg2.grad is not None

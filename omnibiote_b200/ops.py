@@ -10,6 +10,7 @@ import torch
 from . import _lib
 
 EPI_PLAIN, EPI_RESID, EPI_GELU, EPI_GELU_BWD, EPI_RESID_DROPOUT, EPI_ROPE, EPI_ROWMASK = 0, 1, 2, 3, 5, 7, 8
+EPI_GELU_DG, EPI_MUL = 9, 10
 
 # gelu_mode 0: one rounding (TorchScript-fused execution on CUDA); 1: a bf16 rounding per primitive (eager CPU run of
 # the same expression, which is what the CPU oracle does). See SURVEY Appendix A.2.

@@ -107,6 +107,14 @@ def test_gemm_epilogues(cg):
         (x * 0.5 * (1.0 + torch.erf(x / 1.41421))).sum().backward()
         d = ops.gemm(a, b, epilogue=ops.EPI_GELU_BWD, aux_in=u, allow_splitk=False)
         _check(d, ref.to(torch.bfloat16).float() * x.grad, "gelu bwd")
+        # the pair the block uses: forward saves gelu'(U), backward multiplies by it
+        dg = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+        g2 = ops.gemm(a, b, epilogue=ops.EPI_GELU_DG, aux_out=dg, allow_splitk=False)
+        assert torch.equal(g2, g)
+        _check(dg, x.grad, "gelu derivative")
+        d2 = ops.gemm(a, b, epilogue=ops.EPI_MUL, aux_in=dg, allow_splitk=False)
+        _check(d2, ref.to(torch.bfloat16).float() * dg.float(), "mul epilogue")
+        _check(d2, ref.to(torch.bfloat16).float() * x.grad, "gelu bwd via saved derivative", ulps=2)
     finally:
         lib.obt_gemm_set_cta_group(0)
 
