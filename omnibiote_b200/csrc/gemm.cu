@@ -419,6 +419,8 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   p.rope_T = rope_T;
   p.rope_d = rope_head_dim;
   p.rope_cols = rope_cols;
+  p.rope_T_mask = (rope_T > 0 && (rope_T & (rope_T - 1)) == 0) ? rope_T - 1 : -1;
+  p.rope_d_mask = (rope_head_dim > 0 && (rope_head_dim & (rope_head_dim - 1)) == 0) ? rope_head_dim - 1 : -1;
   auto aligned16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
   p.vec_ok = (N % 8 == 0) && (ldd % 8 == 0) && aligned16(D) &&
              (aux_in == nullptr || epilogue == EPI_ROWMASK || (ld_aux_in % 8 == 0 && aligned16(aux_in))) &&
@@ -430,12 +432,26 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   const int slots = sm_count() / cluster;
   const bool splittable = (epilogue == EPI_PLAIN || (epilogue == EPI_RESID && aux_in == D && ld_aux_in == ldd)) &&
                           workspace != nullptr && (M * N) % 4 == 0 && (N % 4 == 0) && (ldd % 4 == 0);
-  if (splittable && tiles * 2 <= slots && p.num_kb >= 16) {
-    int s = slots / tiles;
-    if (s > 8) s = 8;
-    while (s > 1 && (p.num_kb / s) < 4) --s;
-    while (s > 1 && static_cast<long long>(s) * M * N > workspace_elems) --s;
-    p.splits = s;
+  if (splittable && tiles < slots && p.num_kb >= 16) {
+    // Pick the split count with the smallest estimated time: tensor time / wave efficiency + the fp32 partials'
+    // round trip through HBM. (c_attn's weight gradient, 48 tiles on 74 CTA pairs, ran at 65 % occupancy unsplit:
+    // 3 splits = 144 tiles fill 1.95 waves.)
+    const double t_math = 2.0 * static_cast<double>(M) * N * K / 1.45e15;
+    double best = 1e30;
+    int best_s = 1;
+    for (int s = 1; s <= 8; ++s) {
+      if (s > 1 && ((p.num_kb / s) < 4 || static_cast<long long>(s) * M * N > workspace_elems)) break;
+      const int work = tiles * s;
+      const int waves = (work + slots - 1) / slots;
+      const double eff = static_cast<double>(work) / (static_cast<double>(waves) * slots);
+      const double t_io = s > 1 ? (2.0 * s * static_cast<double>(M) * N * 4.0) / 5.0e12 + 4e-6 : 0.0;
+      const double t = t_math / eff + t_io;
+      if (t < best * 0.98) {  // prefer fewer splits unless the gain is real
+        best = t;
+        best_s = s;
+      }
+    }
+    p.splits = best_s;
   }
   p.kb_per_split = (p.num_kb + p.splits - 1) / p.splits;
   // all splits must be non-empty

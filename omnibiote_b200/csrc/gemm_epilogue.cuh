@@ -51,7 +51,15 @@ struct GemmParams {
   const float* rope_cos;
   const float* rope_sin;
   int rope_T, rope_d, rope_cols;
+  int rope_T_mask, rope_d_mask;  // T - 1 / d - 1 when they are powers of two (no integer division in the epilogue), else -1
 };
+
+// offset of the 4 table entries of columns gcol..gcol+7 at row grow
+__device__ __forceinline__ long long rope_table_off(const GemmParams& p, long long grow, int gcol) {
+  const int t = p.rope_T_mask >= 0 ? static_cast<int>(grow) & p.rope_T_mask : static_cast<int>(grow % p.rope_T);
+  const int c = p.rope_d_mask >= 0 ? gcol & p.rope_d_mask : gcol % p.rope_d;
+  return static_cast<long long>(t) * (p.rope_d >> 1) + (c >> 1);
+}
 
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_BN = 256;
@@ -254,7 +262,7 @@ __device__ __noinline__ void epilogue_segment_slow(const GemmParams& p, uint4 w,
   }
   if constexpr (EPI == EPI_ROPE) {  // rope_cols, rope_d are multiples of 8: a chunk is either all rotary or none
     if (gcol < p.rope_cols) {
-      const long long off = (grow % p.rope_T) * (p.rope_d >> 1) + ((gcol % p.rope_d) >> 1);
+      const long long off = rope_table_off(p, grow, gcol);
       const float4 cs = *reinterpret_cast<const float4*>(p.rope_cos + off);
       float4 sn = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.rope_sin != nullptr) sn = *reinterpret_cast<const float4*>(p.rope_sin + off);
@@ -321,7 +329,7 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
             rc[it] = make_float4(1.f, 1.f, 1.f, 1.f);
             rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (grow < p.M && gcol < p.rope_cols) {
-              const long long off = (grow % p.rope_T) * (p.rope_d >> 1) + ((gcol % p.rope_d) >> 1);
+              const long long off = rope_table_off(p, grow, gcol);
               rc[it] = *reinterpret_cast<const float4*>(p.rope_cos + off);
               if (p.rope_sin != nullptr) rs[it] = *reinterpret_cast<const float4*>(p.rope_sin + off);
             }
