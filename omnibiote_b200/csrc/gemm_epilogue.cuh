@@ -109,6 +109,38 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
   dg = fmaf(x * (0.5f * 1.1283791670955126f * inv), e, 0.5f * cdf2);
 }
 
+// Two elements at a time with packed fp32x2 instructions: the polynomial, the squares and the products of the pair
+// cost one instruction instead of two (the GELU forward epilogue is instruction-issue bound: c_fc ran at 225 us
+// against 181 us for mlp.c_proj with the same FLOPs). Same formula and selection as one_plus_erf / gelu_and_grad.
+__device__ __forceinline__ void gelu_and_grad_x2(float x0, float x1, float& g0, float& g1, float& d0, float& d1) {
+  const float inv = 1.0f / 1.41421f;
+  const uint64_t x = f2_pack(x0, x1);
+  const uint64_t t = f2_mul(x, f2_splat(inv));
+  float t0, t1;
+  f2_unpack(t, t0, t1);
+  const uint64_t a = f2_pack(fabsf(t0), fabsf(t1));
+  float den0, den1;
+  f2_unpack(f2_fma(f2_splat(0.3275911f), a, f2_splat(1.0f)), den0, den1);
+  float k0, k1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(k0) : "f"(den0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(k1) : "f"(den1));
+  float q0, q1;
+  f2_unpack(f2_mul(f2_mul(a, a), f2_splat(-1.4426950408889634f)), q0, q1);
+  const float e0 = fast_ex2(q0), e1 = fast_ex2(q1);
+  const uint64_t k = f2_pack(k0, k1), e = f2_pack(e0, e1);
+  uint64_t poly = f2_fma(f2_splat(1.061405429f), k, f2_splat(-1.453152027f));
+  poly = f2_fma(poly, k, f2_splat(1.421413741f));
+  poly = f2_fma(poly, k, f2_splat(-0.284496736f));
+  poly = f2_fma(poly, k, f2_splat(0.254829592f));
+  const uint64_t pe = f2_mul(f2_mul(poly, k), e);                      // 1 - erf(|t|)
+  float pe0, pe1, cp0, cp1;
+  f2_unpack(pe, pe0, pe1);
+  f2_unpack(f2_fma(pe, f2_splat(-1.0f), f2_splat(2.0f)), cp0, cp1);    // 2 - pe
+  const uint64_t cdf2 = f2_pack(t0 >= 0.f ? cp0 : pe0, t1 >= 0.f ? cp1 : pe1);  // 1 + erf(t), no cancellation
+  f2_unpack(f2_mul(f2_mul(x, f2_splat(0.5f)), cdf2), g0, g1);
+  f2_unpack(f2_fma(f2_mul(x, f2_splat(0.5f * 1.1283791670955126f * inv)), e, f2_mul(cdf2, f2_splat(0.5f))), d0, d1);
+}
+
 __device__ __forceinline__ float gelu_grad_ref(float x) {
   const float inv = 1.0f / 1.41421f;
   float cdf2, e;
@@ -184,7 +216,7 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, float (&v)[8]
     }
   } else if constexpr (EPI == EPI_GELU_DG) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) gelu_and_grad(v[e], v[e], u[e]);
+    for (int e = 0; e < 8; e += 2) gelu_and_grad_x2(v[e], v[e + 1], v[e], v[e + 1], u[e], u[e + 1]);
   } else if constexpr (EPI == EPI_MUL) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = v[e] * a[e];
