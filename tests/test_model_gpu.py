@@ -169,3 +169,20 @@ def test_activation_checkpointing_same_gradients(golden):
         grads.append({n: p.grad.clone() for n, p in model.named_parameters()})
     for n in grads[0]:
         assert torch.equal(grads[0][n], grads[1][n]), n
+
+
+def test_reference_checkpoint_pickle_runs_on_the_kernels():
+    """A whole-module pickle of the unmodified reference (tests/golden/ref_checkpoint.pt) is read without the
+    reference's code, moved to the GPU and must reproduce the oracle's logits for the same weights."""
+    import io
+    import os
+    from conftest import GOLDEN
+    from omnibiote_b200 import checkpoint
+    c = torch.load(os.path.join(GOLDEN, "ref_checkpoint.pt"), map_location="cpu", weights_only=False)["bf16"]
+    model = checkpoint.load_reference_checkpoint(io.BytesIO(c["pickle"])).cuda().eval()
+    g = torch.Generator().manual_seed(9)
+    ids = torch.randint(4, 96, (3, 24), generator=g)
+    got = model(ids.cuda()).float().cpu()
+    p = {k: v for k, v in c["state_dict"].items()}
+    want = orc.forward(p, 2, 4, ids, None, readout_width_mult=c["width_mult"]).float()
+    assert rel_err(got, want) < 1.5e-2, rel_err(got, want)
