@@ -177,6 +177,7 @@ def test_reference_checkpoint_pickle_runs_on_the_kernels():
     import io
     import os
     from conftest import GOLDEN
+    import omnibiota_oracle as orc
     from omnibiote_b200 import checkpoint
     c = torch.load(os.path.join(GOLDEN, "ref_checkpoint.pt"), map_location="cpu", weights_only=False)["bf16"]
     model = checkpoint.load_reference_checkpoint(io.BytesIO(c["pickle"])).cuda().eval()
