@@ -138,7 +138,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     // ===================== MMA issuer =====================
     // The whole warp runs the (warp-uniform) control flow and waits; one elected lane issues. Keeping every operand
     // provably uniform lets the compiler feed tcgen05.mma from uniform registers: with `if (lane == 0)` around the
-    // loop it wrapped EVERY MMA in a per-lane R2UR/ELECT waterfall loop (~13 instructions, profiles/r01_attn_v7).
+    // loop it wrapped EVERY MMA in a per-lane R2UR/ELECT waterfall loop (~13 instructions,
+    // profiles/r01_attn_v7_bwd.source.txt).
     const int n_t = __shfl_sync(0xffffffffu, n_tiles, 0);
     const bool leader = elect_one();
     const uint32_t q_addr = smem_u32(sQ);

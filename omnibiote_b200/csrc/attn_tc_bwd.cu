@@ -2,19 +2,22 @@
 //
 //   delta_i = dO_i . O_i                                   (attn_delta_kernel, memory-bound pre-pass)
 //   dQ kernel : one CTA per 128-query tile, loops over 64-key sub-tiles:  S = Q K^T, dP = dO V^T (TMEM),
-//               dS = P o (dP - delta) * scale -> bf16 smem tile,   dQ += dS K   (accumulated in TMEM)
+//               dS = P o (keep o dP - delta) -> bf16 written back over the S columns,   dQ += dS K   (TMEM)
 //   dKV kernel: one CTA per 128-key tile, loops over 64-query sub-tiles: S^T = K Q^T, dP^T = V dO^T (TMEM),
-//               P^T, dS^T -> bf16 smem tiles,   dV += P^T dO,   dK += dS^T Q   (accumulated in TMEM)
+//               P^T, dS^T -> bf16 written back over the score columns,   dV += P^T dO,   dK += dS^T Q   (TMEM)
 // P is recomputed from the forward's (row max, log exp-sum) pair. Splitting dQ from dK/dV recomputes S and dP once
 // more (7 instead of 5 tile products) but needs no atomics and keeps every accumulator in TMEM.
 //
-// Pipelining (v3): the score tiles are 64 wide so that S/dP fit TWICE in TMEM next to the gradient accumulators
-// (2 x 128 + 128 columns for dQ, 2 x 128 + 256 for dV/dK = all 512). The MMA thread issues the score products of
-// sub-tile s+1 before the gradient products of sub-tile s, so the 8 compute warps (two threads per TMEM lane, 32
-// columns each) always have a finished score tile to work on while the tensor pipe is busy (v2 alternated between
-// the two and measured 552 / 789 us per layer, profiles/r01_launches_v3.txt).
-// The Q / dO / K / V smem tiles written by TMA serve both as K-major operands (scores) and, read through an
-// MN-major descriptor, as the [reduction x 128] operands of the gradient products: no transposes are materialised.
+// Common structure: the score tiles are 64 wide so that S/dP fit TWICE in TMEM next to the gradient accumulators
+// (2 x 128 + 128 columns for dQ + 128 for Q and dO, 2 x 128 + 256 for dV/dK = all 512). The MMA warp issues the score
+// products of sub-tile s+1 before the gradient products of sub-tile s, so the 8 compute warps (two threads per TMEM
+// lane, 32 columns each) have a finished score tile to work on while the tensor pipe is busy. Every A operand of a
+// gradient product (dS, P^T, dS^T) - and for dQ also Q and dO - lives in TMEM; K / V / Q / dO tiles written by TMA
+// serve as K-major B operands of the score products and, read through an MN-major descriptor, as the
+// [reduction x 128] B operands of the gradient products: no transposes are materialised, no operand is staged by
+// the compute warps in shared memory. Scalings (softmax scale, 1/(1-p)) are folded into the epilogues, which also
+// apply the rotary adjoint to dQ / dK. 12 warps: warpgroup 0 = TMA producer + MMA issuer (+ 2 idle), warpgroups
+// 1-2 = compute, with register reallocation between them (attn_tc_common.cuh).
 #include "attn_tc_common.cuh"
 
 namespace obt {

@@ -62,14 +62,6 @@ __device__ __forceinline__ void rope_adjoint32(float (&f)[32], const float4* cs,
   }
 }
 
-// byte offset of the 16-byte chunk holding elements [c, c+8) of row r inside a [128 x 128] bf16 tile stored as two
-// [128 x 64] K-major sub-tiles with the 128B swizzle (what TMA SWIZZLE_128B produces and UMMA descriptors expect)
-__device__ __forceinline__ uint32_t sw128_chunk_off(int r, int c) {
-  const int sub = c >> 6;
-  const int chunk = (c & 63) >> 3;
-  return static_cast<uint32_t>(sub * 16384 + r * 128 + ((chunk ^ (r & 7)) << 4));
-}
-
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -89,20 +81,9 @@ __device__ __forceinline__ void issue_scores_128x64(uint32_t d_tmem, uint32_t a_
   }
 }
 
-// D[128 x 128(d)] += A[128 x 64] * B[64 x 128(d)]: A is a K-major [128 x 64] tile (one 128-byte row per lane),
-// B is read MN-major from a TMA-written [64 rows x 128] tile whose two 64-column halves are `b_lbo` bytes apart.
-__device__ __forceinline__ void issue_grad_128x128x64(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t b_lbo,
-                                                      bool accumulate) {
-  constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, true);
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    const uint64_t a_desc = make_smem_desc_sw128(a_addr + kk * 32, 0, 1024);
-    const uint64_t b_desc = make_smem_desc_sw128(b_addr + kk * 2048, b_lbo, 1024);
-    umma_bf16_ss<1>(d_tmem, a_desc, b_desc, idesc, (accumulate || kk > 0) ? 1u : 0u);
-  }
-}
-
-// Same product with A = bf16 [128 x 64] held in TMEM (32 columns, two keys per 32-bit column, lane = row).
+// D[128 x 128(d)] += A[128 x 64] * B[64 x 128(d)]: A = bf16 [128 x 64] held in TMEM (32 columns, two keys per 32-bit
+// column, lane = row); B is read MN-major from a TMA-written [64 rows x 128] tile whose two 64-column halves are `b_lbo`
+// bytes apart.
 __device__ __forceinline__ void issue_pv_ts_128x128x64(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, uint32_t b_lbo,
                                                        bool accumulate) {
   constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, true);
@@ -137,11 +118,6 @@ __device__ __forceinline__ void issue_grad_ts_128x128x64(uint32_t d_tmem, uint32
   }
 }
 
-// byte offset of the 16-byte chunk [c, c+8) of row r in a [128 x 64] bf16 K-major tile (128-byte rows, 128B swizzle)
-__device__ __forceinline__ uint32_t sw128_row64_off(int r, int c) {
-  return static_cast<uint32_t>(r * 128 + (((c >> 3) ^ (r & 7)) << 4));
-}
-
 // bit k set <=> position base + k lies in [lo, hi), k = 0..31
 __device__ __forceinline__ uint32_t interval_bits32(int lo, int hi, int base) {
   const int a = min(max(lo - base, 0), 32), b = min(max(hi - base, 0), 32);
@@ -149,9 +125,6 @@ __device__ __forceinline__ uint32_t interval_bits32(int lo, int hi, int base) {
   const uint32_t upto_b = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
   return upto_b & ~((1u << a) - 1u);  // a < 32 here
 }
-
-// named barrier among the 256 compute threads (warps 2..9)
-__device__ __forceinline__ void compute_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 constexpr int ATT_COMPUTE_WARPS = 8;
 // Backward kernels: 12 warps. Warpgroup 0 = {TMA producer, MMA issuer, 2 idle}, warpgroups 1-2 = the 8 compute warps.
