@@ -67,3 +67,49 @@ def test_no_cpu_fallback():
         ops.gemm(a, a)
     with pytest.raises(RuntimeError):
         ops.layernorm_fwd(a, a[0])
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Argument count and coarse type class (pointer / 64-bit int / 32-bit int / float / double) of every ctypes
+    binding against the C prototype in include/omnibiote_b200.h: an ABI drift between the two corrupts arguments
+    silently."""
+    import ctypes as ct
+    from omnibiote_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "omnibiote_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = dict(re.findall(r"\b(obt_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text))
+
+    def c_class(arg):
+        arg = arg.strip()
+        if arg in ("void", ""):
+            return None
+        if "*" in arg or "cudaStream_t" in arg:
+            return "ptr"
+        if "unsigned long long" in arg or "long long" in arg:
+            return "i64"
+        if "double" in arg:
+            return "f64"
+        if "float" in arg:
+            return "f32"
+        if "int" in arg:
+            return "i32"
+        raise AssertionError(f"unclassified C argument: {arg!r}")
+
+    def py_class(t):
+        if t in (ct.c_void_p, ct.c_char_p):
+            return "ptr"
+        if t in (ct.c_longlong, ct.c_ulonglong):
+            return "i64"
+        if t is ct.c_int:
+            return "i32"
+        if t is ct.c_float:
+            return "f32"
+        if t is ct.c_double:
+            return "f64"
+        raise AssertionError(f"unclassified ctypes type: {t!r}")
+
+    for name, (_res, args) in _lib.SIGNATURES.items():
+        assert name in protos, name
+        want = [c for c in (c_class(a) for a in protos[name].split(",")) if c is not None]
+        got = [py_class(t) for t in args]
+        assert got == want, (name, got, want)
