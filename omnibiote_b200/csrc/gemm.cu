@@ -54,7 +54,10 @@ struct GemmCfg {
 
 template <int kMode, bool kAMN, bool kBMN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ GemmParams p) {
+  // (__grid_constant__: the out-of-line slow-path epilogue takes `p` by reference; without it the whole struct was
+  // copied to the stack and EVERY field access in the epilogue loops became a local-memory load)
   using Cfg = GemmCfg<kMode>;
   constexpr int kCG = Cfg::CG;
   constexpr int kCluster = Cfg::CLUSTER;
