@@ -72,10 +72,15 @@ int obt_embed_bwd(const long long* idx, const void* dout, void* dwte, float* scr
 int obt_layernorm_fwd(const void* x, const void* gamma, void* y, void* z, float* mean, float* rstd, long long M, int C,
                       float eps, float readout_div, cudaStream_t stream);
 int obt_layernorm_bwd_workspace_rows(void);
-/* dx = rb(dres + rb(ln_bwd(rb(dy / dy_div)))); dgamma (+)= rb(sum_rows dy * xhat). workspace fp32 [rows*C]. */
+/* dx = rb(dres + rb(ln_bwd(rb(dy / dy_div)))); dgamma (+)= rb(sum_rows dy * xhat), reduced inside the same launch.
+ * workspace fp32 [32 + rows*C], words 0..1 zero before the first call (the kernel re-zeroes them).
+ * dx_drop (optional, NULL to skip) = dropout replay of dx with (drop_p, seed, offset), the mask of obt_dropout /
+ * GEMM epilogue 5 on the same flat indices: the upstream gradient of the residual branch `x + dropout(f(x))`
+ * (model.py:151,167) whose output this LayerNorm normalised. */
 int obt_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
                       const void* dres, void* dx, void* dgamma, int accumulate_dgamma, float* workspace, long long M,
-                      int C, float dy_div, cudaStream_t stream);
+                      int C, float dy_div, void* dx_drop, float drop_p, unsigned long long seed,
+                      unsigned long long offset, cudaStream_t stream);
 
 /* ---- rotary embedding, in place on the q and k column ranges of the fused qkv buffer (model.py:39-50,108) ------
  * sin_tab == NULL: bf16 model whose complex freqs_cis buffer was cast to a real bf16 table (cosine scaling).
@@ -148,10 +153,11 @@ int obt_mask_compress(const void* mask, long long msb, long long msq, int* lo, i
                       cudaStream_t stream);
 
 /* ---- MLM input masking (train_encoder.py:273-279): mask = Bernoulli(prob) & id != PAD & id != EOS;
- * masked_ids = mask ? MASK : id. Device Philox stream instead of the reference's host numpy RNG. */
+ * masked_ids = mask ? MASK : id. Device Philox stream instead of the reference's host numpy RNG.
+ * counters (optional fp32[2]): += {number of masked positions, number of non-PAD tokens} (train_encoder.py:350). */
 int obt_mlm_mask(const long long* ids, long long* masked_ids, unsigned char* mask, long long n, float prob,
                  unsigned long long seed, unsigned long long offset, long long pad_token, long long eos_token,
-                 long long mask_token, cudaStream_t stream);
+                 long long mask_token, float* counters, cudaStream_t stream);
 
 /* ---- masked-rows-only head (optional path of the training step): d loss / d logits of train_encoder.py:301-305 is
  * exactly zero outside the MLM mask, so ln_f's output rows inside the mask are compacted, the head GEMM, the CE and
@@ -168,13 +174,17 @@ int obt_scatter_rows(const void* src, long long lds, const int* idx, void* dst, 
                      int C, cudaStream_t stream);
 
 /* ---- MLM loss (train_encoder.py:301-305) over materialised logits ----------------------------------------------
- * scalars (device fp32[4]): [0] loss, [1] number of masked tokens, [2] d loss / d CE_t. row_mask: uint8 [M] or NULL. */
+ * scalars (device fp32[4]): [0] loss, [1] number of masked tokens, [2] d loss / d CE_t, [3] n_acc.
+ * row_mask: uint8 [M] or NULL. */
 int obt_ce_fwd(const void* logits, long long ld, const long long* targets, const unsigned char* row_mask, float* lse,
                float* tok_loss, float* scalars, long long M, int V, float n_acc, cudaStream_t stream);
-/* overwrites logits with d loss / d logits (exact zeros on unmasked rows). unmasked_rows_zero != 0: the caller
+/* overwrites logits with d loss / d logits (exact zeros on unmasked rows) for an incoming d loss =
+ * upstream * (upstream_dev ? *upstream_dev : 1); upstream_dev is a bf16 device scalar (autograd's grad of the bf16
+ * loss) or NULL. unmasked_rows_zero != 0: the caller
  * guarantees those rows already hold zeros (head GEMM with epilogue 8), so they are neither read nor written. */
 int obt_ce_bwd(void* logits, long long ld, const long long* targets, const unsigned char* row_mask, const float* lse,
-               const float* scalars, float upstream, long long M, int V, int unmasked_rows_zero, cudaStream_t stream);
+               const float* scalars, float upstream, const void* upstream_dev, long long M, int V,
+               int unmasked_rows_zero, cudaStream_t stream);
 
 /* ---- clip_grad_norm_ (train_encoder.py:316) + MuAdamW step (train_encoder.py:199,317) --------------------------
  * metas: device array of {void* p, g, m, v; int64 numel; float lr, wd} (obt_opt_meta_bytes() each);
@@ -184,8 +194,8 @@ int obt_opt_meta_bytes(void);
 int obt_grad_norm(const void* metas, const int* blk_tensor, const long long* blk_off, int n_blocks, float gscale,
                   float max_norm, float* partial, float* norm_out, cudaStream_t stream);
 int obt_adamw_step(const void* metas, const int* blk_tensor, const long long* blk_off, int n_blocks,
-                   const float* clip_scalars, float gscale, float lr_mult, double beta1, double beta2, double eps, int step,
-                   int zero_grad, cudaStream_t stream);
+                   const float* clip_scalars, const int* skip_flag, float gscale, float lr_mult, double beta1,
+                   double beta2, double eps, int step, int zero_grad, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ SIGNATURES = {
     "obt_embed_bwd": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, f32, u64, u64, vp]),
     "obt_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, f32, f32, vp]),
     "obt_layernorm_bwd_workspace_rows": (i32, []),
-    "obt_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, f32, vp]),
+    "obt_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, f32, vp, f32, u64, u64, vp]),
     "obt_rope": (i32, [vp, vp, vp, i64, i32, i32, i32, i64, i32, vp]),
     "obt_dropout": (i32, [vp, vp, i64, f32, u64, u64, vp]),
     "obt_scale_div": (i32, [vp, vp, i64, f32, vp]),
@@ -47,16 +47,16 @@ SIGNATURES = {
     "obt_pad_mask_intervals": (i32, [vp, vp, vp, i32, i32, i64, vp]),
     "obt_mask_from_intervals": (i32, [vp, vp, vp, i32, i32, vp]),
     "obt_mask_compress": (i32, [vp, i64, i64, vp, vp, vp, i32, i32, vp]),
-    "obt_mlm_mask": (i32, [vp, vp, vp, i64, f32, u64, u64, i64, i64, i64, vp]),
+    "obt_mlm_mask": (i32, [vp, vp, vp, i64, f32, u64, u64, i64, i64, i64, vp, vp]),
     "obt_compact_rows": (i32, [vp, vp, i64, i32, vp, vp, vp, vp, vp]),
     "obt_gather_rows": (i32, [vp, i64, vp, vp, i64, i32, i32, vp]),
     "obt_scatter_rows": (i32, [vp, i64, vp, vp, i64, i64, i32, i32, vp]),
     "obt_ce_fwd": (i32, [vp, i64, vp, vp, vp, vp, vp, i64, i32, f32, vp]),
-    "obt_ce_bwd": (i32, [vp, i64, vp, vp, vp, vp, f32, i64, i32, i32, vp]),
+    "obt_ce_bwd": (i32, [vp, i64, vp, vp, vp, vp, f32, vp, i64, i32, i32, vp]),
     "obt_opt_chunk_elems": (i32, []),
     "obt_opt_meta_bytes": (i32, []),
     "obt_grad_norm": (i32, [vp, vp, vp, i32, f32, f32, vp, vp, vp]),
-    "obt_adamw_step": (i32, [vp, vp, vp, i32, vp, f32, f32, c_double, c_double, c_double, i32, i32, vp]),
+    "obt_adamw_step": (i32, [vp, vp, vp, i32, vp, vp, f32, f32, c_double, c_double, c_double, i32, i32, vp]),
 }
 
 

@@ -4,6 +4,7 @@ nvcc cross-compiles without a GPU; the resulting ``.so`` is git-ignored but trav
 """
 from __future__ import annotations
 
+import fcntl
 import hashlib
 import os
 import shutil
@@ -54,8 +55,22 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every .cu under csrc/ and link the shared library. Returns the library path."""
     if not force and not needs_build():
         return LIB_PATH
-    nvcc = _nvcc()
     BUILD_DIR.mkdir(exist_ok=True)
+    # one builder at a time: under torchrun every rank gets here on a fresh checkout; the others wait on the lock and
+    # then find the finished library (the link goes to a temporary name and is renamed into place, so a concurrent
+    # dlopen never sees a half-written file)
+    with open(BUILD_DIR / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB_PATH
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
+    nvcc = _nvcc()
     headers_mtime = max(p.stat().st_mtime for p in CSRC.glob("*.cuh"))
 
     def compile_one(src: Path) -> Path:
@@ -75,10 +90,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-cudart", "static"]
+    tmp_lib = BUILD_DIR / f"libomnibiote_b200.{os.getpid()}.so.tmp"
+    cmd = [nvcc, "-shared", "-o", str(tmp_lib), *map(str, objs), "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp_lib, LIB_PATH)
     (BUILD_DIR / "digest.txt").write_text(_digest())
     return LIB_PATH
 

@@ -88,6 +88,7 @@ __global__ void ce_fwd_kernel(const __nv_bfloat16* __restrict__ logits, long lon
 // scalars[0] = loss = rb( rb(sum_t rb(rb(tok_t / n_acc) * m_t)) / count )   (train_encoder.py:301-305, all bf16)
 // scalars[1] = count = sum_t m_t
 // scalars[2] = g = rb(rb(1/count) / n_acc)   gradient of the loss w.r.t. every masked token's CE term
+// scalars[3] = n_acc (kept for the backward: an upstream factor u turns g into rb(rb(u/count) / n_acc))
 __global__ void ce_reduce_kernel(const float* __restrict__ tok_loss, const unsigned char* __restrict__ row_mask,
                                  long long M, float n_acc, float* __restrict__ scalars) {
   __shared__ float sbuf[32];
@@ -103,14 +104,19 @@ __global__ void ce_reduce_kernel(const float* __restrict__ tok_loss, const unsig
     scalars[0] = rb(rb(s) / cnt);
     scalars[1] = cnt;
     scalars[2] = rb(rb(1.0f / cnt) / n_acc);
+    scalars[3] = n_acc;
   }
 }
 
-// dlogits[row, j] = rb( (exp(logit_j - lse) - [j == target]) * g * upstream ) for masked rows, exact zeros otherwise.
+// dlogits[row, j] = rb( (exp(logit_j - lse) - [j == target]) * g ) for masked rows, exact zeros otherwise, with
+// g = rb(rb(u / count) / n_acc) and u = upstream * (upstream_dev ? float(*upstream_dev) : 1): the autograd chain of
+// train_encoder.py:301-305 for an incoming d loss = u (u = 1 reproduces scalars[2]). upstream_dev is a bf16 device
+// scalar (the dtype of the loss), so that `(k * loss).backward()` needs no host synchronisation.
 // Written in place over the logits buffer.
 __global__ void ce_bwd_kernel(__nv_bfloat16* __restrict__ logits, long long ld, const long long* __restrict__ targets,
                               const unsigned char* __restrict__ row_mask, const float* __restrict__ lse_in,
-                              const float* __restrict__ scalars, float upstream, int V, int unmasked_rows_zero) {
+                              const float* __restrict__ scalars, float upstream,
+                              const __nv_bfloat16* __restrict__ upstream_dev, int V, int unmasked_rows_zero) {
   const long long row = blockIdx.x;
   __nv_bfloat16* x = logits + row * ld;
   if (row_mask && row_mask[row] == 0) {
@@ -118,7 +124,8 @@ __global__ void ce_bwd_kernel(__nv_bfloat16* __restrict__ logits, long long ld, 
     for (int c = threadIdx.x; c < V / 8; c += blockDim.x) reinterpret_cast<uint4*>(x)[c] = make_uint4(0, 0, 0, 0);
     return;
   }
-  const float g = scalars[2] * upstream;
+  const float up = upstream_dev ? upstream * __bfloat162float(*upstream_dev) : upstream;
+  const float g = (up == 1.0f) ? scalars[2] : rb(rb(up / scalars[1]) / scalars[3]);
   const float lse = lse_in[row];
   const int y = static_cast<int>(targets[row]);
   for (int c = threadIdx.x; c < V / 8; c += blockDim.x) {
@@ -198,8 +205,10 @@ __global__ void gradnorm_final_kernel(const float* __restrict__ partial, int n, 
   if (threadIdx.x == 0) {
     const float norm = sqrtf(s);
     out[0] = norm;
-    float coef = max_norm / (norm + 1e-6f);
-    out[1] = (max_norm > 0.f) ? fminf(coef, 1.0f) : 1.0f;
+    // torch.clamp(coef, max=1.0) propagates a NaN norm (fminf would turn it into 1): a non-finite gradient then
+    // poisons the step visibly, as it does in the reference, instead of being applied unclipped
+    const float coef = max_norm / (norm + 1e-6f);
+    out[1] = (max_norm > 0.f) ? ((coef != coef) ? coef : fminf(coef, 1.0f)) : 1.0f;
   }
 }
 
@@ -209,16 +218,20 @@ __global__ void gradnorm_final_kernel(const float* __restrict__ partial, int n, 
 //   p  = rb(p * (1 - lr*wd))
 //   m  = rb(m + (1-b1)*(g - m))
 //   v  = rb(rb(v*b2) + (1-b2)*g*g)
-//   den= rb(rb(rb(sqrt(v)) / sqrt(1-b2^t)) + eps)
+//   den= rb(rb(rb(sqrt(v)) / sqrt(1-b2^t)) + eps)     (the division as a multiplication by the host-side reciprocal)
 //   p  = rb(p - (lr/(1-b1^t)) * (m / den))
-__global__ void adamw_kernel(const ParamMeta* __restrict__ metas, const int* __restrict__ blk_tensor,
-                             const long long* __restrict__ blk_off, const float* __restrict__ clip_scalars,
-                             float gscale, float lr_mult, float one_minus_b1, float beta2, float one_minus_b2,
-                             float eps, float bc1, float bc2_sqrt, int zero_grad) {
+__global__ void __launch_bounds__(256)
+adamw_kernel(const ParamMeta* __restrict__ metas, const int* __restrict__ blk_tensor,
+             const long long* __restrict__ blk_off, const float* __restrict__ clip_scalars,
+             const int* __restrict__ skip_flag, float gscale, float lr_mult, float one_minus_b1, float beta2,
+             float one_minus_b2, float eps, float bc1, float inv_bc2_sqrt, int zero_grad) {
   const ParamMeta pm = metas[blk_tensor[blockIdx.x]];
   const long long off = blk_off[blockIdx.x];
   const long long n = min(static_cast<long long>(OPT_CHUNK), pm.numel - off);
   const float clip = clip_scalars ? clip_scalars[1] : 1.0f;
+  // skip_flag != 0: the gradients of this step are known to be incomplete (masked-rows head overflow); parameters and
+  // moments stay untouched, the gradient buffer is still cleared
+  const bool skip = skip_flag != nullptr && *skip_flag != 0;
   const float lr = pm.lr * lr_mult;
   const float decay = 1.0f - lr * pm.wd;
   const float step = lr / bc1;
@@ -226,22 +239,22 @@ __global__ void adamw_kernel(const ParamMeta* __restrict__ metas, const int* __r
   __nv_bfloat16* G = pm.g + off;
   __nv_bfloat16* Mm = pm.m + off;
   __nv_bfloat16* Vv = pm.v + off;
+  // The kernel was instruction-issue bound at 51 % of the HBM peak (IEEE sqrt and two IEEE divisions per element):
+  // sqrt.approx / rcp-based division are exact to ~2^-22, i.e. invisible after the bf16 rounding that follows each
+  // of them except on rounding ties (<= 1 bf16 ulp, the tolerance of the reference-golden test).
   auto upd = [&](float& p, float g, float& m, float& v) {
     g = gscale == 1.0f ? g : rb(g * gscale);
     g = rb(g * clip);
     p = rb(p * decay);
     m = rb(m + one_minus_b1 * (g - m));
     v = rb(rb(v * beta2) + one_minus_b2 * g * g);
-    const float den = rb(rb(rb(sqrtf(v)) / bc2_sqrt) + eps);
-    p = rb(p - step * (m / den));
+    float sq;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));
+    const float den = rb(rb(rb(sq) * inv_bc2_sqrt) + eps);
+    p = rb(p - step * __fdividef(m, den));
   };
-  const bool aligned = ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(G) |
-                         reinterpret_cast<uintptr_t>(Mm) | reinterpret_cast<uintptr_t>(Vv)) & 15) == 0;
-  const long long n8 = aligned ? n / 8 : 0;
-  for (long long i = threadIdx.x; i < n8; i += blockDim.x) {
-    uint4 up = reinterpret_cast<uint4*>(P)[i], ug = reinterpret_cast<uint4*>(G)[i];
-    uint4 um = reinterpret_cast<uint4*>(Mm)[i], uv = reinterpret_cast<uint4*>(Vv)[i];
-    uint32_t* wp = &up.x; uint32_t* wg = &ug.x; uint32_t* wm = &um.x; uint32_t* wv = &uv.x;
+  auto upd8 = [&](uint4& up, const uint4& ug, uint4& um, uint4& uv) {
+    uint32_t* wp = &up.x; const uint32_t* wg = &ug.x; uint32_t* wm = &um.x; uint32_t* wv = &uv.x;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float p0 = bf16_lo(wp[j]), p1 = bf16_hi(wp[j]);
@@ -253,18 +266,48 @@ __global__ void adamw_kernel(const ParamMeta* __restrict__ metas, const int* __r
       wm[j] = pack_bf16x2(m0, m1);
       wv[j] = pack_bf16x2(v0, v1);
     }
-    reinterpret_cast<uint4*>(P)[i] = up;
-    reinterpret_cast<uint4*>(Mm)[i] = um;
-    reinterpret_cast<uint4*>(Vv)[i] = uv;
-    if (zero_grad) reinterpret_cast<uint4*>(G)[i] = make_uint4(0, 0, 0, 0);
+  };
+  const bool aligned = ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(G) |
+                         reinterpret_cast<uintptr_t>(Mm) | reinterpret_cast<uintptr_t>(Vv)) & 15) == 0;
+  const long long n8 = aligned ? n / 8 : 0;
+  uint4* P4 = reinterpret_cast<uint4*>(P);
+  uint4* G4 = reinterpret_cast<uint4*>(G);
+  uint4* M4 = reinterpret_cast<uint4*>(Mm);
+  uint4* V4 = reinterpret_cast<uint4*>(Vv);
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  if (skip) {
+    if (zero_grad) {
+      for (long long i = threadIdx.x; i < n8; i += blockDim.x) G4[i] = zero4;
+      for (long long i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) G[i] = __float2bfloat16_rn(0.f);
+    }
+    return;
   }
-  for (long long i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) {
-    float p = __bfloat162float(P[i]), m = __bfloat162float(Mm[i]), v = __bfloat162float(Vv[i]);
-    upd(p, __bfloat162float(G[i]), m, v);
-    P[i] = __float2bfloat16_rn(p);
-    Mm[i] = __float2bfloat16_rn(m);
-    Vv[i] = __float2bfloat16_rn(v);
-    if (zero_grad) G[i] = __float2bfloat16_rn(0.f);
+  // two 16-byte vectors of each of the four streams in flight per thread (8 independent loads before any math)
+  long long i = threadIdx.x;
+  for (; i + blockDim.x < n8; i += 2 * blockDim.x) {
+    const long long k = i + blockDim.x;
+    uint4 up0 = P4[i], ug0 = G4[i], um0 = M4[i], uv0 = V4[i];
+    uint4 up1 = P4[k], ug1 = G4[k], um1 = M4[k], uv1 = V4[k];
+    upd8(up0, ug0, um0, uv0);
+    P4[i] = up0; M4[i] = um0; V4[i] = uv0;
+    if (zero_grad) G4[i] = zero4;
+    upd8(up1, ug1, um1, uv1);
+    P4[k] = up1; M4[k] = um1; V4[k] = uv1;
+    if (zero_grad) G4[k] = zero4;
+  }
+  for (; i < n8; i += blockDim.x) {
+    uint4 up = P4[i], ug = G4[i], um = M4[i], uv = V4[i];
+    upd8(up, ug, um, uv);
+    P4[i] = up; M4[i] = um; V4[i] = uv;
+    if (zero_grad) G4[i] = zero4;
+  }
+  for (long long j = n8 * 8 + threadIdx.x; j < n; j += blockDim.x) {
+    float p = __bfloat162float(P[j]), m = __bfloat162float(Mm[j]), v = __bfloat162float(Vv[j]);
+    upd(p, __bfloat162float(G[j]), m, v);
+    P[j] = __float2bfloat16_rn(p);
+    Mm[j] = __float2bfloat16_rn(m);
+    Vv[j] = __float2bfloat16_rn(v);
+    if (zero_grad) G[j] = __float2bfloat16_rn(0.f);
   }
 }
 
@@ -287,13 +330,14 @@ extern "C" int obt_ce_fwd(const void* logits, long long ld, const long long* tar
 }
 
 extern "C" int obt_ce_bwd(void* logits, long long ld, const long long* targets, const unsigned char* row_mask,
-                          const float* lse, const float* scalars, float upstream, long long M, int V,
-                          int unmasked_rows_zero, cudaStream_t stream) {
+                          const float* lse, const float* scalars, float upstream, const void* upstream_dev,
+                          long long M, int V, int unmasked_rows_zero, cudaStream_t stream) {
   OBT_REQUIRE(logits && targets && lse && scalars, "obt_ce_bwd: null pointer");
   OBT_REQUIRE(V % 8 == 0 && ld % 8 == 0, "obt_ce_bwd: V=%d ld=%lld must be multiples of 8", V, ld);
   OBT_REQUIRE(M > 0 && M < (1ll << 31), "obt_ce_bwd: bad M=%lld", M);
   ce_bwd_kernel<<<static_cast<unsigned>(M), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(logits), ld, targets,
-                                                             row_mask, lse, scalars, upstream, V,
+                                                             row_mask, lse, scalars, upstream,
+                                                             static_cast<const __nv_bfloat16*>(upstream_dev), V,
                                                              unmasked_rows_zero);
   return check_launch("ce_bwd");
 }
@@ -315,16 +359,16 @@ extern "C" int obt_grad_norm(const void* metas, const int* blk_tensor, const lon
 }
 
 extern "C" int obt_adamw_step(const void* metas, const int* blk_tensor, const long long* blk_off, int n_blocks,
-                              const float* clip_scalars, float gscale, float lr_mult, double beta1, double beta2,
-                              double eps, int step, int zero_grad, cudaStream_t stream) {
+                              const float* clip_scalars, const int* skip_flag, float gscale, float lr_mult,
+                              double beta1, double beta2, double eps, int step, int zero_grad, cudaStream_t stream) {
   OBT_REQUIRE(metas && blk_tensor && blk_off, "obt_adamw_step: null pointer");
   OBT_REQUIRE(n_blocks > 0 && step >= 1, "obt_adamw_step: bad n_blocks=%d step=%d", n_blocks, step);
   const float bc1 = static_cast<float>(1.0 - pow(beta1, static_cast<double>(step)));
-  const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(beta2, static_cast<double>(step))));
+  const float inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(1.0 - pow(beta2, static_cast<double>(step))));
   // (1 - beta) is formed in double like the reference's Python floats, then narrowed once
   adamw_kernel<<<n_blocks, 256, 0, stream>>>(static_cast<const ParamMeta*>(metas), blk_tensor, blk_off, clip_scalars,
-                                             gscale, lr_mult, static_cast<float>(1.0 - beta1),
+                                             skip_flag, gscale, lr_mult, static_cast<float>(1.0 - beta1),
                                              static_cast<float>(beta2), static_cast<float>(1.0 - beta2),
-                                             static_cast<float>(eps), bc1, bc2_sqrt, zero_grad);
+                                             static_cast<float>(eps), bc1, inv_bc2_sqrt, zero_grad);
   return check_launch("adamw");
 }

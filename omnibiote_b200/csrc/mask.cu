@@ -190,7 +190,9 @@ extern "C" int obt_mask_compress(const void* mask, long long msb, long long msq,
 namespace obt {
 __global__ void mlm_mask_kernel(const long long* __restrict__ ids, long long* __restrict__ masked,
                                 unsigned char* __restrict__ mask, long long n, float prob, unsigned long long seed,
-                                unsigned long long offset, long long pad, long long eos, long long mask_token) {
+                                unsigned long long offset, long long pad, long long eos, long long mask_token,
+                                float* __restrict__ counters) {
+  int n_masked = 0, n_tokens = 0;
   for (long long i4 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i4 * 4 < n;
        i4 += static_cast<long long>(gridDim.x) * blockDim.x) {
     uint4 r = philox4x32(seed, static_cast<unsigned long long>(i4), offset);
@@ -203,6 +205,21 @@ __global__ void mlm_mask_kernel(const long long* __restrict__ ids, long long* __
       const bool m = ((w[e] >> 8) * (1.0f / 16777216.0f) < prob) && id != pad && id != eos;
       mask[i] = m ? 1 : 0;
       masked[i] = m ? mask_token : id;
+      n_masked += m ? 1 : 0;
+      n_tokens += (id != pad) ? 1 : 0;
+    }
+  }
+  // step bookkeeping of train_encoder.py:350 (`(input_ids != PAD_TOKEN).sum()`) without a host round trip: integer
+  // counts accumulated in fp32 (exact below 2^24, so the atomic order does not matter)
+  if (counters != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      n_masked += __shfl_xor_sync(0xffffffffu, n_masked, o);
+      n_tokens += __shfl_xor_sync(0xffffffffu, n_tokens, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (n_masked) atomicAdd(counters + 0, static_cast<float>(n_masked));
+      if (n_tokens) atomicAdd(counters + 1, static_cast<float>(n_tokens));
     }
   }
 }
@@ -210,7 +227,7 @@ __global__ void mlm_mask_kernel(const long long* __restrict__ ids, long long* __
 
 extern "C" int obt_mlm_mask(const long long* ids, long long* masked_ids, unsigned char* mask, long long n, float prob,
                             unsigned long long seed, unsigned long long offset, long long pad_token, long long eos_token,
-                            long long mask_token, cudaStream_t stream) {
+                            long long mask_token, float* counters, cudaStream_t stream) {
   OBT_REQUIRE(ids && masked_ids && mask, "obt_mlm_mask: null pointer");
   OBT_REQUIRE(prob >= 0.f && prob <= 1.f, "obt_mlm_mask: prob=%f", prob);
   if (n == 0) return OBT_OK;
@@ -218,7 +235,7 @@ extern "C" int obt_mlm_mask(const long long* ids, long long* masked_ids, unsigne
   const long long cap = static_cast<long long>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
   obt::mlm_mask_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(ids, masked_ids, mask, n, prob, seed, offset,
-                                                                        pad_token, eos_token, mask_token);
+                                                                        pad_token, eos_token, mask_token, counters);
   return check_launch("mlm_mask");
 }
 

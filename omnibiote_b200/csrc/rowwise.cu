@@ -203,15 +203,24 @@ __global__ void ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bf
   }
 }
 
-// LayerNorm backward (dy is first divided by dy_div and rounded: the MuReadout 1/width_mult adjoint). dx = rb( (dres ? dres : 0) + rb(rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat))) )
-// dgamma partial sums (fp32) are written per block into dgamma_partial[gridDim.x][C].
+// LayerNorm backward (dy is first divided by dy_div and rounded: the MuReadout 1/width_mult adjoint).
+//   dx = rb( (dres ? dres : 0) + rb(rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat))) )
+//   dx_drop (optional) = dropout-replay of dx with (drop_p, seed, offset) keyed by the flat element index: the
+//     gradient entering the `x + dropout(f(x))` branch that produced this LayerNorm's input (model.py:151,167), i.e.
+//     the operand of that branch's dgrad / wgrad GEMMs. Writing it here saves the stand-alone dropout kernel's
+//     re-read of dx (profiles/r01_launches_v7.txt: 2 x 24 us per layer).
+//   dgamma (+)= rb(sum_rows dy * xhat): per-block fp32 partials go to dgamma_partial[gridDim.x][C]; the first
+//     ceil(C/32) blocks then wait until every block has published its partial and reduce 32 columns each, in block
+//     order (deterministic). This tail replaces the separate ln_dgamma_reduce launch (10.5 us x 17 per micro-batch).
+//     No deadlock: a waiting block only occupies its own slot, every other block runs to completion without it.
 template <int kMaxChunks>
 __global__ void __launch_bounds__(256, kMaxChunks == 4 ? 2 : 1)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
-                              const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean_in,
-                              const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ dres,
-                              __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma_partial, long long M, int C,
-                              float dy_div) {
+              const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean_in,
+              const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ dres,
+              __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop, float* __restrict__ dgamma_partial,
+              unsigned int* __restrict__ sync_counter, __nv_bfloat16* __restrict__ dgamma, int accumulate_dgamma,
+              long long M, int C, float dy_div, float drop_p, unsigned long long seed, unsigned long long offset) {
   // dgamma partial sums live in shared memory, laid out [warp][chunk i][j][lane] (lane fastest: conflict-free), so
   // the row loop needs ~70 registers and three 256-thread blocks fit per SM (the register-resident version ran one
   // block per SM and reached 1.6 TB/s; see profiles/r01_launches_v3.txt).
@@ -220,6 +229,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nchunks = C / 8;
+  const float drop_scale = 1.0f / (1.0f - drop_p);
   float* my_dg = s_dg + static_cast<size_t>(warp) * kMaxChunks * 256;
 #pragma unroll
   for (int i = 0; i < kMaxChunks; ++i)
@@ -272,6 +282,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     s1 = warp_sum(s1) / C;
     s2 = warp_sum(s2) / C;
     uint4* dst = reinterpret_cast<uint4*>(dx + row * C);
+    uint4* ddst = dx_drop ? reinterpret_cast<uint4*>(dx_drop + row * C) : nullptr;
 #pragma unroll
     for (int i = 0; i < kMaxChunks; ++i) {
       const int c = lane + 32 * i;
@@ -286,7 +297,23 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
           const float xh = (xv[j] - mean) * rstd;
           o[j] = rb(rstd * (d[j] * g[j] - s1 - xh * s2)) + r[j];
         }
-        dst[c] = pack8(o);
+        const uint4 packed = pack8(o);
+        dst[c] = packed;
+        if (ddst) {
+          // same mask as dropout_kernel / the GEMM's EPI_RESID_DROPOUT: one RNG call per 4 consecutive flat elements
+          float q[8];
+          unpack8(packed, q);  // the bf16-rounded dx, exactly what the stand-alone kernel would read back
+          bool k0[4], k1[4];
+          const unsigned long long e4 = (static_cast<unsigned long long>(row) * C + c * 8) >> 2;
+          dropout4(seed, offset, e4, drop_p, k0);
+          dropout4(seed, offset, e4 + 1, drop_p, k1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            q[j] = k0[j] ? q[j] * drop_scale : 0.f;
+            q[4 + j] = k1[j] ? q[4 + j] * drop_scale : 0.f;
+          }
+          ddst[c] = pack8(q);
+        }
       }
     }
   }
@@ -301,27 +328,51 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
       dgamma_partial[static_cast<long long>(blockIdx.x) * C + col] = acc;
     }
   }
-}
-
-// dgamma[c] = rb( (accumulate ? dgamma[c] : 0) + rb(sum_b partial[b][c]) )
-__global__ void ln_dgamma_reduce_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ dgamma, int nblk,
-                                        int C, int accumulate) {
-  // block (32, 8): 32 columns x 8 row groups; coalesced 128-byte reads per row
-  __shared__ float s[8][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  const int ry = threadIdx.y;
-  float t = 0.f;
-  if (c < C)
-    for (int b = ry; b < nblk; b += 8) t += partial[static_cast<long long>(b) * C + c];
-  s[ry][threadIdx.x] = t;
+  // publish, then the first ceil(C/32) blocks reduce 32 columns each once all partials are visible
+  __threadfence();
   __syncthreads();
-  if (ry == 0 && c < C) {
-    float tot = 0.f;
+  if (threadIdx.x == 0) atomicAdd(sync_counter, 1u);
+  const int n_reducers = (C + 31) / 32;
+  if (static_cast<int>(blockIdx.x) >= n_reducers) return;
+  if (threadIdx.x == 0) {
+    // bounded: a stale counter (only possible after an aborted launch) must not hang the device
+    unsigned int spins = 0;
+    while (*reinterpret_cast<volatile unsigned int*>(sync_counter) < gridDim.x) {
+      __nanosleep(64);
+      if (++spins > (1u << 24)) __trap();
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  {
+    // 256 threads = 32 columns x 8 row groups; 128-byte coalesced reads per partial row
+    float* red = s_dg;  // reuse: [8][33]
+    const int tx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + tx;
+    float t = 0.f;
+    if (col < C && ry < 8)
+      for (int bk = ry; bk < static_cast<int>(gridDim.x); bk += 8)
+        t += __ldcg(dgamma_partial + static_cast<long long>(bk) * C + col);
+    if (ry < 8) red[ry * 33 + tx] = t;
+    __syncthreads();
+    if (ry == 0 && col < C) {
+      float tot = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) tot += s[k][threadIdx.x];
-    float o = rb(tot);
-    if (accumulate) o += __bfloat162float(dgamma[c]);
-    dgamma[c] = __float2bfloat16_rn(o);
+      for (int k = 0; k < 8; ++k) tot += red[k * 33 + tx];
+      float o = rb(tot);
+      if (accumulate_dgamma) o += __bfloat162float(dgamma[col]);
+      dgamma[col] = __float2bfloat16_rn(o);
+    }
+  }
+  // the last reducer to finish re-arms the counter for the next launch on this stream
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(sync_counter + 1, 1u) + 1u;
+    if (done == static_cast<unsigned int>(min(n_reducers, static_cast<int>(gridDim.x)))) {
+      sync_counter[0] = 0u;
+      sync_counter[1] = 0u;
+      __threadfence();
+    }
   }
 }
 
@@ -534,33 +585,45 @@ extern "C" int obt_layernorm_fwd(const void* x, const void* gamma, void* y, void
   return check_launch("ln_fwd");
 }
 
-// workspace: fp32 [obt_layernorm_bwd_workspace_rows() * C]
+// workspace: fp32 [32 + obt_layernorm_bwd_workspace_rows() * C]; the first two words are the grid-sync counters of the
+// fused dgamma reduction and MUST be zero before the first call (the kernel leaves them zero again); the per-block
+// partial sums start at word 32 (128-byte aligned).
 extern "C" int obt_layernorm_bwd_workspace_rows(void) { return sm_count() * 4; }
 
 extern "C" int obt_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
                                  const void* dres, void* dx, void* dgamma, int accumulate_dgamma, float* workspace,
-                                 long long M, int C, float dy_div, cudaStream_t stream) {
+                                 long long M, int C, float dy_div, void* dx_drop, float drop_p,
+                                 unsigned long long seed, unsigned long long offset, cudaStream_t stream) {
   OBT_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && workspace, "obt_layernorm_bwd: null pointer");
   OBT_REQUIRE(C % 8 == 0 && C <= 2048, "obt_layernorm_bwd: C=%d must be a multiple of 8 and <= 2048", C);
+  OBT_REQUIRE(M > 0, "obt_layernorm_bwd: empty input");
+  OBT_REQUIRE(dx_drop == nullptr || (drop_p > 0.f && drop_p < 1.f), "obt_layernorm_bwd: drop_p=%f with dx_drop", drop_p);
   const int wpb = (C <= 1024) ? 8 : 4;  // 32 KB of dgamma staging per block either way
-  int grid = sm_count() * 4;
+  const int max_grid = sm_count() * 4;
+  int grid = max_grid;
   if (M < static_cast<long long>(grid) * wpb) grid = static_cast<int>((M + wpb - 1) / wpb);
   if (grid < 1) grid = 1;
+  // the reducer blocks (the first ceil(C/32)) must exist: with very few rows the grid is padded (row loop is a no-op)
+  const int n_reducers = (C + 31) / 32;
+  if (grid < n_reducers) grid = n_reducers;
+  OBT_REQUIRE(grid <= max_grid, "obt_layernorm_bwd: C=%d needs more reducer blocks than the workspace has rows", C);
   const size_t smem = static_cast<size_t>(wpb) * ((C <= 1024) ? 4 : 8) * 256 * sizeof(float);
   auto a = static_cast<const __nv_bfloat16*>(dy);
   auto b = static_cast<const __nv_bfloat16*>(x);
   auto g = static_cast<const __nv_bfloat16*>(gamma);
   auto r = static_cast<const __nv_bfloat16*>(dres);
   auto o = static_cast<__nv_bfloat16*>(dx);
+  auto od = static_cast<__nv_bfloat16*>(dx_drop);
+  auto dg = static_cast<__nv_bfloat16*>(dgamma);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
+  float* partial = workspace + 32;
   if (C <= 1024)
-    ln_bwd_kernel<4><<<grid, wpb * 32, smem, stream>>>(a, b, g, mean, rstd, r, o, workspace, M, C, dy_div);
+    ln_bwd_kernel<4><<<grid, wpb * 32, smem, stream>>>(a, b, g, mean, rstd, r, o, od, partial, counter, dg,
+                                                       accumulate_dgamma, M, C, dy_div, drop_p, seed, offset);
   else
-    ln_bwd_kernel<8><<<grid, wpb * 32, smem, stream>>>(a, b, g, mean, rstd, r, o, workspace, M, C, dy_div);
-  int rc = check_launch("ln_bwd");
-  if (rc) return rc;
-  ln_dgamma_reduce_kernel<<<(C + 31) / 32, dim3(32, 8), 0, stream>>>(workspace, static_cast<__nv_bfloat16*>(dgamma),
-                                                                     grid, C, accumulate_dgamma);
-  return check_launch("ln_dgamma_reduce");
+    ln_bwd_kernel<8><<<grid, wpb * 32, smem, stream>>>(a, b, g, mean, rstd, r, o, od, partial, counter, dg,
+                                                       accumulate_dgamma, M, C, dy_div, drop_p, seed, offset);
+  return check_launch("ln_bwd");
 }
 
 extern "C" int obt_rope(void* qkv, const float* cos_tab, const float* sin_tab, long long M, int T, int C, int head_dim,

@@ -46,6 +46,33 @@ def _grads_final(params) -> None:
         _GRAD_SINK.notify(params)
 
 
+# Dropout replays produced ahead of time by the LayerNorm backward of the NEXT stage (block l+1's ln_1, or ln_f in the
+# head): block l's backward needs dropout(dx2, its mlp seeds) as the operand of its first two GEMMs, and the kernel that
+# writes dx2 can emit it in the same pass (ops.layernorm_bwd(drop=...)). Keyed by the data pointer of dx2; the entry
+# holds dx2 itself, so the address cannot be recycled while the entry exists. A miss (gradient accumulated by autograd,
+# foreign caller, ...) falls back to the stand-alone dropout kernel. Cleared at the start of every forward.
+_DROP_STASH: dict = {}
+
+
+def clear_drop_stash() -> None:
+    _DROP_STASH.clear()
+
+
+def _stash_dropped(dx: torch.Tensor, dx_drop, seeds) -> None:
+    if dx_drop is not None:
+        _DROP_STASH[dx.data_ptr()] = (dx, dx_drop, seeds)
+
+
+def _take_dropped(dx: torch.Tensor, seeds):
+    ent = _DROP_STASH.pop(dx.data_ptr(), None)
+    if ent is None:
+        return None
+    src, dropped, ent_seeds = ent
+    if ent_seeds != seeds or src.shape != dx.shape or src._version != dx._version:
+        return None
+    return dropped
+
+
 def _wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, param):
     """dW[N,K] = dy[M,N]^T @ x[M,K] (both operands MN-major for the tensor cores, no transposes materialised)."""
     if _DIRECT_GRAD and param is not None and param.grad is not None:
@@ -94,14 +121,20 @@ class BlockFunction(torch.autograd.Function):
     """x -> x + attn(ln_1(x)) -> (+ mlp(ln_2(.)))  (model.py:170-181). x is [M, C] with M = B*T."""
 
     @staticmethod
-    def forward(ctx, x, g1, w_qkv, w_o, g2, w_fc, w_pr, cos_tab, sin_tab, mask, B, T, H, p_drop, training):
+    def forward(ctx, x, g1, w_qkv, w_o, g2, w_fc, w_pr, cos_tab, sin_tab, mask, B, T, H, p_drop, training, seeds=None,
+                up_drop=None):
+        """seeds: three (seed, offset) pairs (attention P, attention residual, MLP residual) drawn by the caller, or
+        None to draw them here. up_drop = (p, seed, offset) of the dropout that produced `x` in the previous block
+        (its MLP residual dropout): this block's backward then also emits the replayed gradient for that block."""
         M, C = x.shape
         d = C // H
         p = float(p_drop) if training else 0.0
         dev = x.device
-        seeds = [(0, 0)] * 3
         if p > 0.0:
-            seeds = [ops.philox_args(dev, 4) for _ in range(3)]  # attn P, attn resid, mlp resid
+            if seeds is None:
+                seeds = [ops.philox_args(dev, 4) for _ in range(3)]  # attn P, attn resid, mlp resid
+        else:
+            seeds = [(0, 0)] * 3
         scale = 8.0 / C  # model.py:119,135: 8 / n_embd, independent of n_head
 
         h1, _, mean1, rstd1 = ops.layernorm_fwd(x, g1)
@@ -129,6 +162,7 @@ class BlockFunction(torch.autograd.Function):
         ctx.mask = mask
         ctx.keep = keep
         ctx.meta = (B, T, H, d, p, seeds, scale)
+        ctx.up_drop = up_drop if (up_drop is not None and up_drop[0] > 0.0) else None
         ctx.fused_dg = fused_dg
         ctx.params = (g1, w_qkv, w_o, g2, w_fc, w_pr)
         return x2
@@ -144,17 +178,24 @@ class BlockFunction(torch.autograd.Function):
         direct = _DIRECT_GRAD
 
         # ---- MLP branch: x2 = x1 + dropout(g @ Wpr^T)
-        d_dd = ops.dropout(dx2, p, *seeds[2]) if p > 0.0 else dx2
+        d_dd = dx2
+        if p > 0.0:
+            # usually already written by the LayerNorm backward that produced dx2 (next block's ln_1 or the head's ln_f)
+            d_dd = _take_dropped(dx2, (p, *seeds[2]))
+            if d_dd is None:
+                d_dd = ops.dropout(dx2, p, *seeds[2])
         dw_pr = _wgrad(d_dd, g, ppr)
         du = ops.gemm(d_dd, w_pr, b_mn=True, epilogue=ops.EPI_MUL if ctx.fused_dg else ops.EPI_GELU_BWD, aux_in=u)
         dw_fc = _wgrad(du, h2, pfc)
         dh2 = ops.gemm(du, w_fc, b_mn=True)
         acc2 = direct and pg2.grad is not None
-        dx1, dg2 = ops.layernorm_bwd(dh2, x1, g2, mean2, rstd2, dres=dx2, dgamma=pg2.grad if acc2 else None,
-                                     accumulate_dgamma=acc2)
+        # the same pass also writes dropout(dx1) with the attention-residual mask: the operand of the next two GEMMs
+        dx1, dg2, d_a = ops.layernorm_bwd(dh2, x1, g2, mean2, rstd2, dres=dx2, dgamma=pg2.grad if acc2 else None,
+                                          accumulate_dgamma=acc2, drop=(p, *seeds[1]))
+        if d_a is None:
+            d_a = dx1
 
         # ---- attention branch: x1 = x + dropout(y @ Wo^T)
-        d_a = ops.dropout(dx1, p, *seeds[1]) if p > 0.0 else dx1
         dw_o = _wgrad(d_a, y, po)
         dy = ops.gemm(d_a, w_o, b_mn=True)
         # rotary adjoint fused into the dQ / dK epilogues: dqkv is the gradient of c_attn's raw output
@@ -162,11 +203,12 @@ class BlockFunction(torch.autograd.Function):
         dw_qkv = _wgrad(dqkv, h1, pqkv)
         dh1 = ops.gemm(dqkv, w_qkv, b_mn=True)
         acc1 = direct and pg1.grad is not None
-        dx, dg1 = ops.layernorm_bwd(dh1, x, g1, mean1, rstd1, dres=dx1, dgamma=pg1.grad if acc1 else None,
-                                    accumulate_dgamma=acc1)
+        dx, dg1, dx_drop = ops.layernorm_bwd(dh1, x, g1, mean1, rstd1, dres=dx1, dgamma=pg1.grad if acc1 else None,
+                                             accumulate_dgamma=acc1, drop=ctx.up_drop or (0.0, 0, 0))
+        _stash_dropped(dx, dx_drop, ctx.up_drop)
         _grads_final(ctx.params)
         return (dx, None if acc1 else dg1, dw_qkv, dw_o, None if acc2 else dg2, dw_fc, dw_pr, None, None, None, None,
-                None, None, None, None)
+                None, None, None, None, None, None)
 
 
 class LayerNormFunction(torch.autograd.Function):
@@ -213,13 +255,15 @@ class ReadoutFunction(torch.autograd.Function):
 class HeadLossFunction(torch.autograd.Function):
     """ln_f -> MuReadout -> masked-LM cross-entropy in one schedule (model.py:248-254 + train_encoder.py:301-305).
 
-    The logits (M x V bf16) are materialised once; the CE backward overwrites them in place with d loss / d logits
-    during the forward (rows outside the MLM mask are exact zeros, as in the reference), and the two head GEMMs of
-    the backward consume that buffer. Returns the bf16-rounded scalar loss of the reference.
+    The logits (M x V bf16) are materialised once; the backward overwrites them in place with d loss / d logits
+    (rows outside the MLM mask are exact zeros, as in the reference; the incoming d loss is read on the device, so
+    ``(k * loss).backward()`` and loss scalers work) and the two head GEMMs consume that buffer. Returns the
+    bf16-rounded scalar loss of the reference. The saved logits are consumed by the first backward: a second one
+    through the same graph (retain_graph=True) raises.
     """
 
     @staticmethod
-    def forward(ctx, x, gamma, weight, div, targets, loss_mask, n_acc):
+    def forward(ctx, x, gamma, weight, div, targets, loss_mask, n_acc, up_drop=None):
         emb, z, mean, rstd = ops.layernorm_fwd(x, gamma, readout_div=div)
         del emb
         # the full [M, V] head GEMM; rows outside the loss mask are stored as the zeros d loss / d logits needs there
@@ -227,26 +271,34 @@ class HeadLossFunction(torch.autograd.Function):
         row_mask = loss_mask.reshape(-1).to(torch.uint8).contiguous()
         logits = ops.gemm(z, weight, epilogue=ops.EPI_ROWMASK, aux_in=row_mask)
         scalars, lse, tok, row_mask, tgt = ops.ce_fwd(logits, targets, row_mask, n_acc)
-        ops.ce_bwd_(logits, tgt, row_mask, lse, scalars, 1.0, unmasked_rows_zero=True)
-        ctx.save_for_backward(x, gamma, weight, mean, rstd, z, logits)
+        ctx.save_for_backward(x, gamma, weight, mean, rstd, z, logits, lse, row_mask, tgt, scalars)
         ctx.div = div
         ctx.params = (gamma, weight)
+        ctx.up_drop = up_drop if (up_drop is not None and up_drop[0] > 0.0) else None
+        ctx.consumed = False
         ctx.mark_non_differentiable(scalars)
         loss = scalars[0].to(torch.bfloat16)
         return loss, scalars
 
     @staticmethod
     def backward(ctx, dloss, _dscalars):
-        x, gamma, weight, mean, rstd, z, dlogits = ctx.saved_tensors
+        x, gamma, weight, mean, rstd, z, logits, lse, row_mask, tgt, scalars = ctx.saved_tensors
+        if ctx.consumed:
+            raise RuntimeError("omnibiote_b200: the MLM head's logits buffer was overwritten by the first backward; "
+                               "a second backward through the same graph is not supported")
+        ctx.consumed = True
         pg, pw = ctx.params
-        # `loss.backward()` feeds exactly 1; any other upstream factor is folded in afterwards on the small tensors.
+        # d loss / d logits for the incoming d loss (a bf16 device scalar), in place over the logits
+        dlogits = ops.ce_bwd_(logits, tgt, row_mask, lse, scalars, 1.0, unmasked_rows_zero=True,
+                              upstream_dev=dloss.to(torch.bfloat16))
         dw = _wgrad(dlogits, z, pw)
         dz = ops.gemm(dlogits, weight, b_mn=True)
         acc = _DIRECT_GRAD and pg.grad is not None
-        dx, dg = ops.layernorm_bwd(dz, x, gamma, mean, rstd, dgamma=pg.grad if acc else None, accumulate_dgamma=acc,
-                                   dy_div=ctx.div)
+        dx, dg, dx_drop = ops.layernorm_bwd(dz, x, gamma, mean, rstd, dgamma=pg.grad if acc else None,
+                                            accumulate_dgamma=acc, dy_div=ctx.div, drop=ctx.up_drop or (0.0, 0, 0))
+        _stash_dropped(dx, dx_drop, ctx.up_drop)
         _grads_final(ctx.params)
-        return dx, (None if acc else dg), dw, None, None, None, None
+        return dx, (None if acc else dg), dw, None, None, None, None, None
 
 
 class HeadLossMaskedRowsFunction(torch.autograd.Function):
@@ -261,7 +313,7 @@ class HeadLossMaskedRowsFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, gamma, weight, div, targets, loss_mask, n_acc, cap):
+    def forward(ctx, x, gamma, weight, div, targets, loss_mask, n_acc, cap, up_drop=None):
         emb, z, mean, rstd = ops.layernorm_fwd(x, gamma, readout_div=div)
         del emb
         idx, tgt_c, valid_c, meta = ops.compact_rows(loss_mask, targets, cap)
@@ -269,26 +321,33 @@ class HeadLossMaskedRowsFunction(torch.autograd.Function):
         del z
         logits = ops.gemm(zc, weight)
         scalars, lse, tok, row_mask, tgt = ops.ce_fwd(logits, tgt_c, valid_c, n_acc)
-        ops.ce_bwd_(logits, tgt, row_mask, lse, scalars, 1.0)
-        ctx.save_for_backward(x, gamma, weight, mean, rstd, zc, logits, idx)
+        ctx.save_for_backward(x, gamma, weight, mean, rstd, zc, logits, idx, lse, row_mask, tgt, scalars)
         ctx.div = div
         ctx.params = (gamma, weight)
+        ctx.up_drop = up_drop if (up_drop is not None and up_drop[0] > 0.0) else None
+        ctx.consumed = False
         ctx.mark_non_differentiable(scalars, meta)
         loss = scalars[0].to(torch.bfloat16)
         return loss, scalars, meta
 
     @staticmethod
     def backward(ctx, dloss, _dscalars, _dmeta):
-        x, gamma, weight, mean, rstd, zc, dlogits, idx = ctx.saved_tensors
+        x, gamma, weight, mean, rstd, zc, logits, idx, lse, row_mask, tgt, scalars = ctx.saved_tensors
+        if ctx.consumed:
+            raise RuntimeError("omnibiote_b200: the MLM head's logits buffer was overwritten by the first backward; "
+                               "a second backward through the same graph is not supported")
+        ctx.consumed = True
         pg, pw = ctx.params
+        dlogits = ops.ce_bwd_(logits, tgt, row_mask, lse, scalars, 1.0, upstream_dev=dloss.to(torch.bfloat16))
         dw = _wgrad(dlogits, zc, pw)
         dzc = ops.gemm(dlogits, weight, b_mn=True)
         dz = ops.scatter_rows(dzc, idx, x.shape[0])
         acc = _DIRECT_GRAD and pg.grad is not None
-        dx, dg = ops.layernorm_bwd(dz, x, gamma, mean, rstd, dgamma=pg.grad if acc else None, accumulate_dgamma=acc,
-                                   dy_div=ctx.div)
+        dx, dg, dx_drop = ops.layernorm_bwd(dz, x, gamma, mean, rstd, dgamma=pg.grad if acc else None,
+                                            accumulate_dgamma=acc, dy_div=ctx.div, drop=ctx.up_drop or (0.0, 0, 0))
+        _stash_dropped(dx, dx_drop, ctx.up_drop)
         _grads_final(ctx.params)
-        return dx, (None if acc else dg), dw, None, None, None, None, None
+        return dx, (None if acc else dg), dw, None, None, None, None, None, None
 
 
 def masked_rows_capacity(n_rows: int, mask_prob: float, sigmas: float = 8.0) -> int:

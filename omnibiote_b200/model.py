@@ -120,7 +120,9 @@ class Block(nn.Module):
         self.ln_2 = LayerNorm(config.n_embd, bias=config.bias)
         self.mlp = MLP(config)
 
-    def forward(self, x, attn_mask=None):
+    def forward(self, x, attn_mask=None, seeds=None, up_drop=None):
+        """seeds / up_drop: dropout bookkeeping supplied by OmniBioTA._trunk (see functional.BlockFunction.forward);
+        a stand-alone call leaves them None and the block draws its own seeds."""
         _require_cuda_bf16(x, "Block input")
         B, T, C = x.shape
         H = self.attn.n_head
@@ -130,7 +132,8 @@ class Block(nn.Module):
         mask = attn_mask if isinstance(attn_mask, ops.MaskSpec) else ops.MaskSpec(attn_mask, B, H, T)
         out = Fn.BlockFunction.apply(
             x.reshape(B * T, C), self.ln_1.weight, self.attn.c_attn.weight, self.attn.c_proj.weight, self.ln_2.weight,
-            self.mlp.c_fc.weight, self.mlp.c_proj.weight, cos, sin, mask, B, T, H, self.attn.dropout, self.training)
+            self.mlp.c_fc.weight, self.mlp.c_proj.weight, cos, sin, mask, B, T, H, self.attn.dropout, self.training,
+            seeds, up_drop)
         return out.view(B, T, C)
 
 
@@ -161,6 +164,7 @@ class OmniBioTA(nn.Module):
             ln_f=LayerNorm(config.n_embd, bias=config.bias),
         ))
         self.lm_head = MuReadout(config.n_embd, config.vocab_size, bias=False)
+        self._last_drop = None
 
         print("number of parameters: %.2fM" % (self.get_num_params() / 1e6,))
 
@@ -172,7 +176,8 @@ class OmniBioTA(nn.Module):
 
     # ------------------------------------------------------------------------------------------------------------
     def _trunk(self, idx, attn_mask):
-        """Embedding + all blocks; returns the pre-ln_f residual stream (b, t, C)."""
+        """Embedding + all blocks; returns the pre-ln_f residual stream (b, t, C). ``self._last_drop`` is left holding
+        the (p, seed, offset) of the last block's MLP residual dropout (None without dropout) for the fused head."""
         if idx.dim() != 2:
             raise RuntimeError(f"omnibiote_b200: idx must be (b, t), got {tuple(idx.shape)}")
         b, t = idx.size()
@@ -192,11 +197,20 @@ class OmniBioTA(nn.Module):
         else:
             mask = ops.MaskSpec(attn_mask, b, blocks[0].attn.n_head, t) if len(blocks) else None
         ckpt = self.config.checkpoint_freq
+        # Dropout seeds are drawn here, not inside the blocks, so that block l+1 knows the mask of block l's MLP
+        # residual dropout: its LayerNorm backward then writes the replayed gradient block l needs in the same pass
+        # (functional._DROP_STASH). Plain arguments, so activation-checkpoint recomputation replays them unchanged.
+        Fn.clear_drop_stash()
+        up_drop = None
         for i, block in enumerate(blocks):
+            p = float(block.attn.dropout) if self.training else 0.0
+            seeds = [ops.philox_args(x.device, 4) for _ in range(3)] if p > 0.0 else None
             if ckpt > 0 and i % ckpt == 0 and torch.is_grad_enabled():
-                x = checkpoint(block, x, mask, use_reentrant=False)
+                x = checkpoint(block, x, mask, seeds, up_drop, use_reentrant=False)
             else:
-                x = block(x, attn_mask=mask)
+                x = block(x, attn_mask=mask, seeds=seeds, up_drop=up_drop)
+            up_drop = (p, *seeds[2]) if p > 0.0 else None
+        self._last_drop = up_drop
         return x
 
     def forward(self, idx, attn_mask=None, return_embeddings=False):
@@ -242,10 +256,10 @@ class OmniBioTA(nn.Module):
             loss, scalars, meta = Fn.HeadLossMaskedRowsFunction.apply(
                 x.reshape(b * t, C), self.transformer.ln_f.weight, self.lm_head.weight,
                 float(self.lm_head.readout_div()), targets.reshape(-1), loss_mask.reshape(-1), float(n_accum),
-                int(masked_rows_cap))
+                int(masked_rows_cap), self._last_drop)
             self.head_rows_meta = meta
             return loss, scalars
         loss, scalars = Fn.HeadLossFunction.apply(
             x.reshape(b * t, C), self.transformer.ln_f.weight, self.lm_head.weight, float(self.lm_head.readout_div()),
-            targets.reshape(-1), loss_mask.reshape(-1), float(n_accum))
+            targets.reshape(-1), loss_mask.reshape(-1), float(n_accum), self._last_drop)
         return loss, scalars

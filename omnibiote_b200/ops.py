@@ -143,6 +143,16 @@ def embed_fwd(idx: torch.Tensor, wte: torch.Tensor, drop_p: float = 0.0, seed: i
     return out
 
 
+def check_embedding_ids(device) -> None:
+    """Host check (synchronises) of the flag obt_embed_fwd raises for token ids outside [0, vocab): the kernel reads
+    row 0 for such ids instead of faulting like nn.Embedding's device assert, so callers poll this at logging cadence."""
+    err = _workspaces.get(("embed_err", torch.int32, device))
+    if err is not None and int(err.item()) != 0:
+        err.zero_()
+        raise RuntimeError("omnibiote_b200: token id outside the vocabulary reached the embedding "
+                           "(corrupt shard or wrong vocab_size?)")
+
+
 def embed_bwd(idx: torch.Tensor, dout: torch.Tensor, dwte: torch.Tensor, accumulate: bool, drop_p: float = 0.0,
               seed: int = 0, offset: int = 0) -> None:
     _req(dout, "dout")
@@ -172,8 +182,11 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-5, reado
     return y, z, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, dgamma=None, accumulate_dgamma=False, dy_div: float = 1.0):
-    """Returns (dx, dgamma). dx = rb(dres + rb(ln_bwd(rb(dy / dy_div))))."""
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, dgamma=None, accumulate_dgamma=False, dy_div: float = 1.0,
+                  drop: tuple | None = None):
+    """Returns (dx, dgamma) or, with drop=(p, seed, offset), (dx, dgamma, dx_drop).
+    dx = rb(dres + rb(ln_bwd(rb(dy / dy_div)))); dx_drop = dropout(dx, p, seed, offset) (same mask as ops.dropout and
+    the GEMM's EPI_RESID_DROPOUT): the gradient entering the dropped residual branch that produced x."""
     _req(dy, "ln dy")
     M, C = x.shape
     lib = _lib.load()
@@ -181,11 +194,18 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, dgamma=None, accumulate_d
     if dgamma is None:
         dgamma = torch.empty(C, dtype=torch.bfloat16, device=x.device)
         accumulate_dgamma = False
-    ws = workspace("ln_bwd", lib.obt_layernorm_bwd_workspace_rows() * C, torch.float32, x.device)
+    # words 0..1 = grid-sync counters of the fused dgamma reduction (zero on entry, re-zeroed by the kernel)
+    ws = workspace("ln_bwd", 32 + lib.obt_layernorm_bwd_workspace_rows() * max(C, 2048), torch.float32, x.device, zero=True)
+    dx_drop, p, seed, off = None, 0.0, 0, 0
+    if drop is not None and drop[0] > 0.0:
+        p, seed, off = drop
+        dx_drop = torch.empty_like(x)
     rc = lib.obt_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                _ptr(dres), dx.data_ptr(), dgamma.data_ptr(), int(accumulate_dgamma), ws.data_ptr(), M, C,
-                               float(dy_div), _stream())
+                               float(dy_div), _ptr(dx_drop), float(p), seed, off, _stream())
     _lib.check(rc, "obt_layernorm_bwd")
+    if drop is not None:
+        return dx, dgamma, dx_drop
     return dx, dgamma
 
 
@@ -418,12 +438,19 @@ def ce_fwd(logits: torch.Tensor, targets: torch.Tensor, row_mask: torch.Tensor |
     return scalars, lse, tok, row_mask, targets
 
 
-def ce_bwd_(logits, targets, row_mask, lse, scalars, upstream: float = 1.0, unmasked_rows_zero: bool = False):
+def ce_bwd_(logits, targets, row_mask, lse, scalars, upstream: float = 1.0, unmasked_rows_zero: bool = False,
+            upstream_dev: torch.Tensor | None = None):
+    """In place: logits <- d loss / d logits for an incoming d loss = upstream * (upstream_dev or 1); upstream_dev is a
+    bf16 device scalar (autograd's gradient of the bf16 loss), read by the kernel without a host synchronisation."""
     logits, ld = _mat(logits, "logits")
     M, V = logits.shape
+    if upstream_dev is not None:
+        _req(upstream_dev, "upstream gradient")
+        if upstream_dev.numel() != 1:
+            raise RuntimeError("omnibiote_b200: the upstream gradient of the loss must be a scalar")
     rc = _lib.load().obt_ce_bwd(logits.data_ptr(), ld, targets.data_ptr(), _ptr(row_mask), lse.data_ptr(),
-                                scalars.data_ptr(), float(upstream), M, V, int(unmasked_rows_zero and row_mask is not None),
-                                _stream())
+                                scalars.data_ptr(), float(upstream), _ptr(upstream_dev), M, V,
+                                int(unmasked_rows_zero and row_mask is not None), _stream())
     _lib.check(rc, "obt_ce_bwd")
     return logits
 

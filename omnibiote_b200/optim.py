@@ -22,10 +22,21 @@ class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
+        self._init_runtime_state()
+
+    def _init_runtime_state(self):
         self._plan_key = None
         self._plan = None
         self._global_step = 0
         self.last_grad_norm = None  # device tensor [norm, clip_coef] of the latest clip_and_step
+
+    def __setstate__(self, state):
+        # torch.save(optimizer) / torch.load (the reference's checkpoint and resume format, train_encoder.py:209,413)
+        # keeps only defaults / state / param_groups: the launch plan and its device buffers are rebuilt lazily
+        super().__setstate__(state)
+        self._init_runtime_state()
+        steps = [int(st["step"]) for st in self.state.values() if "step" in st]
+        self._global_step = max(steps) if steps else 0
 
     # -- block plan: which chunk of which tensor each CUDA block processes (depends on shapes only) --------------
     def _build_plan(self, params):
@@ -77,11 +88,14 @@ class FusedAdamW(torch.optim.Optimizer):
         return params, lrs, wds, betas, eps
 
     @torch.no_grad()
-    def clip_and_step(self, max_norm: float | None = None, grad_scale: float = 1.0, zero_grad: bool = False):
+    def clip_and_step(self, max_norm: float | None = None, grad_scale: float = 1.0, zero_grad: bool = False,
+                      skip_flag: torch.Tensor | None = None):
         """clip_grad_norm_(params, max_norm) + AdamW step in one pass over the gradients.
 
         grad_scale multiplies every gradient first (e.g. 1/world_size after a sum all-reduce);
-        zero_grad=True also clears the gradient buffers in place (keeps their addresses stable)."""
+        zero_grad=True also clears the gradient buffers in place (keeps their addresses stable);
+        skip_flag: optional int32 device scalar, non-zero = leave parameters and moments untouched this step (the
+        gradients are known to be incomplete); decided on the device, no host synchronisation."""
         params, lrs, wds, betas, eps = self._collect()
         if not params:
             return None
@@ -115,19 +129,26 @@ class FusedAdamW(torch.optim.Optimizer):
         for p in params:
             self.state[p]["step"] += 1
         step = int(self.state[params[0]]["step"].item())
+        if skip_flag is not None and (not skip_flag.is_cuda or skip_flag.dtype != torch.int32):
+            raise RuntimeError("FusedAdamW: skip_flag must be an int32 CUDA tensor")
         rc = lib.obt_adamw_step(plan["metas_dev"].data_ptr(), plan["blk_tensor"].data_ptr(), plan["blk_off"].data_ptr(),
-                                plan["n_blocks"], clip_ptr, float(grad_scale), 1.0, float(betas[0]), float(betas[1]),
-                                float(eps), step, int(zero_grad), stream)
+                                plan["n_blocks"], clip_ptr, 0 if skip_flag is None else skip_flag.data_ptr(),
+                                float(grad_scale), 1.0, float(betas[0]), float(betas[1]), float(eps), step,
+                                int(zero_grad), stream)
         _lib.check(rc, "obt_adamw_step")
         return self.last_grad_norm
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, *, max_norm: float | None = None, grad_scale: float = 1.0, zero_grad: bool = False,
+             skip_flag: torch.Tensor | None = None):
+        """``optimizer.step()`` of the reference (train_encoder.py:317); the keyword arguments fold the preceding
+        ``clip_grad_norm_`` (:316) and the DDP mean into the same pass (see clip_and_step). Going through ``step`` keeps
+        torch's LR-scheduler bookkeeping (it wraps this method) intact."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        self.clip_and_step(None)
+        self.clip_and_step(max_norm, grad_scale=grad_scale, zero_grad=zero_grad, skip_flag=skip_flag)
         return loss
 
 

@@ -56,6 +56,9 @@ class FlatGradBuckets:
         self._pending = []
         self._ready_count = [0] * len(bucket_param_groups)
         self._armed = False
+        # CUDA events around the compute stream's wait for the side stream in finish(): the part of the all-reduce that
+        # the backward did not hide (read with exposed_ms(); recording costs nothing on the device)
+        self._wait_events = None
 
     # ---- overlap protocol: arm() before the last micro-batch's backward, notify() as gradients become final -----
     def arm(self):
@@ -95,22 +98,41 @@ class FlatGradBuckets:
             else:
                 for bi in range(len(self.bucket_sizes)):
                     self._launch(bi)
+            timed = self.comm_stream is not None and self.flat.is_cuda
+            if timed:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             for w in self._pending:
                 w.wait()
             if self.comm_stream is not None:
                 torch.cuda.current_stream().wait_stream(self.comm_stream)
+            if timed:
+                e1.record()
+                self._wait_events = (e0, e1)
         self._pending = []
         self._armed = False
+
+    def exposed_ms(self) -> float:
+        """Milliseconds the compute stream spent waiting for the gradient all-reduce at the end of the latest step
+        (synchronises; 0 without a process group)."""
+        if self._wait_events is None:
+            return 0.0
+        e0, e1 = self._wait_events
+        e1.synchronize()
+        return float(e0.elapsed_time(e1))
 
     def zero_(self):
         self.flat.zero_()
 
 
-def model_buckets(model):
-    """Backward-order buckets for OmniBioTA: [ln_f + lm_head], blocks from last to first (two per bucket), [wte]."""
+def model_buckets(model, blocks_per_bucket: int = 1):
+    """Backward-order buckets for OmniBioTA: [ln_f + lm_head], blocks from last to first, [wte].
+    One block per bucket (25 MB for the small shape, 101 MB for the large one): the all-reduce of everything but the
+    embedding is in flight long before the backward ends, and the last block's bucket — the one whose transfer can only
+    start when the backward is nearly over — stays small."""
     buckets = [[model.transformer.ln_f.weight, model.lm_head.weight]]
     blocks = list(model.transformer.h)[::-1]
-    for i in range(0, len(blocks), 2):
-        buckets.append([p for blk in blocks[i:i + 2] for p in blk.parameters()])
+    for i in range(0, len(blocks), blocks_per_bucket):
+        buckets.append([p for blk in blocks[i:i + blocks_per_bucket] for p in blk.parameters()])
     buckets.append([model.transformer.wte.weight])
     return buckets

@@ -66,10 +66,58 @@ def main():
         b = q.grad.float() / world
         worst = max(worst, float((a - b).norm() / (b.norm() + 1e-30)))
     ok = worst < 1.5e-2
+
+    # ---- the drop-in module wrapped in stock torch DistributedDataParallel, exactly as train_encoder.py:185 does
+    # (no no_sync(): DDP's reducer hooks fire on the custom autograd Functions' parameter gradients and average over
+    # ranks); the reference's own loss expression on the dense logits (train_encoder.py:301-305)
+    ddp_model = make_model(2, 256, H, vocab, T, seed=rank).train()
+    ddp_model.load_state_dict(model.state_dict())
+    ddp = torch.nn.parallel.DistributedDataParallel(ddp_model, device_ids=[local])
+    y, m = ids_all[rank], lm_all[rank]
+    lo, hi = ops.doc_mask_intervals(y, 3, False)
+    mask4 = ops.mask_from_intervals(lo, hi).unsqueeze(1).expand(-1, H, -1, -1)
+    logits = ddp(y.masked_fill(m, 2), attn_mask=mask4)
+    ce = torch.nn.functional.cross_entropy(logits.view(-1, logits.size(-1)), y.view(-1), reduction="none")
+    ce = ce * m.view(-1).float()
+    (ce.sum() / m.view(-1).sum()).backward()
+    worst_ddp = 0.0
+    for (n, p), (_, q) in zip(ddp_model.named_parameters(), ref_model.named_parameters()):
+        a = p.grad.float()                      # DDP already averaged over ranks
+        b = q.grad.float() / world
+        worst_ddp = max(worst_ddp, float((a - b).norm() / (b.norm() + 1e-30)))
+    ok = ok and worst_ddp < 2.5e-2
+
+    # ---- MLMTrainer across ranks: identical parameters after a step on every rank, and the step bookkeeping
+    # ([loss_sum, n_masked, n_tokens] in ONE async NCCL all-reduce instead of the reference's two Gloo gathers)
+    from omnibiote_b200.train import MLMTrainer
+    tr_model = make_model(2, 256, H, vocab, T, seed=rank).train()
+    tr_model.load_state_dict(model.state_dict())
+    tr = MLMTrainer(tr_model, global_batch=world * 2 * mbs, mini_batch_size=mbs, ctx_len=T, lr=1e-3, token_budget=1e9)
+    gi = torch.Generator().manual_seed(1000 + rank)
+    my_ids = torch.randint(20, vocab, (2 * mbs, T), generator=gi)
+    my_ids[:, T // 2] = 3
+    my_ids[0, T - 10 * (rank + 1):] = 1                     # some PAD, a different amount on every rank
+    my_ids = my_ids.to(dev)
+    torch.manual_seed(77 + rank)
+    local_loss = tr.step(my_ids)
+    stats = tr.read_stats()
+    gathered = [torch.zeros(2, device=dev) for _ in range(world)]
+    dist.all_gather(gathered, torch.cat([local_loss.float().reshape(1),
+                                         (my_ids != 1).sum().float().reshape(1)]))
+    want_loss = float(sum(g[0] for g in gathered)) / world
+    want_tokens = int(sum(g[1] for g in gathered))
+    ok = ok and abs(stats["loss"] - want_loss) <= 1e-5 * abs(want_loss) and stats["n_tokens"] == want_tokens
+    ok = ok and stats["tokens_seen"] == want_tokens and stats["n_masked"] > 0
+    sums = torch.stack([p.detach().float().sum() for p in tr_model.parameters()])
+    lo_, hi_ = sums.clone(), sums.clone()
+    dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    ok = ok and bool(torch.equal(lo_, hi_))                 # every rank applied the same update
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"worst relative gradient difference {worst:.2e}")
+        print(f"worst relative gradient difference: flat buckets {worst:.2e}, torch DDP wrapper {worst_ddp:.2e}; "
+              f"step stats {stats} (want loss {want_loss:.6f}, tokens {want_tokens})")
         print("DDP_OK" if float(flag) == 1.0 else "DDP_MISMATCH")
     dist.destroy_process_group()
     sys.exit(0 if float(flag) == 1.0 else 1)

@@ -41,3 +41,26 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 
 def max_abs(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
+
+
+def make_model(n_layer, n_head, n_embd, vocab_size=512, block_size=256, dropout=0.0, seed=0, checkpoint_freq=0):
+    """Random-init OmniBioTA on the B200 kernels with the reference's muP setup (train_encoder.py:145-170):
+    target / base (n_embd 24, 3 heads) / delta (n_embd 48, 12 heads) models, set_base_shapes, bf16."""
+    import contextlib
+    import copy
+    import io
+    import warnings
+    from omnibiote_b200.model import OmniBioTA, OmniBioTAConfig
+    from omnibiote_b200.mup import set_base_shapes
+    cfg = OmniBioTAConfig()
+    cfg.vocab_size, cfg.block_size, cfg.n_layer, cfg.n_head, cfg.n_embd = vocab_size, block_size, n_layer, n_head, n_embd
+    cfg.dropout, cfg.checkpoint_freq, cfg.flash = dropout, checkpoint_freq, True
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = OmniBioTA(cfg)
+        c2 = copy.copy(cfg); c2.n_embd, c2.n_head = 24, 3
+        c3 = copy.copy(cfg); c3.n_embd, c3.n_head = 48, 12
+        set_base_shapes(m, OmniBioTA(c2), delta=OmniBioTA(c3))
+        m.to(torch.bfloat16)
+    return m

@@ -19,6 +19,34 @@ def test_flop_model_is_the_references_formula():
     assert n == bench.N_NONEMB_SMALL
 
 
+def test_parameter_count_and_flop_model_of_both_configs():
+    assert bench.n_nonembedding(bench.SMALL) == bench.N_NONEMB_SMALL
+    # SURVEY §8d / BASELINE.md §2: large (32L / 2048 / 16h): N = 1 744 963 584, 11 275 087 872 FLOP per token
+    assert bench.n_nonembedding(bench.LARGE) == 1_744_963_584
+    assert bench.flops_per_token(32, 2048, 1024, bench.n_nonembedding(bench.LARGE)) == 11_275_087_872
+    # encode (forward, no head): 234 881 024 FLOP per token at T = 1024, 335 544 320 at T = 4096
+    assert bench.encode_flops_per_token(bench.SMALL, 1024) == 234_881_024
+    assert bench.encode_flops_per_token(bench.SMALL, 4096) == 335_544_320
+
+
+def test_both_arms_report_the_same_config():
+    a = bench.workload_config("small", 1024, 32, 0.1, 1)
+    assert a["global_batch"] == 1024 and a["mini_batch_size"] == 32 and a["grad_accum_per_rank"] == 32
+    assert a["seq_len"] == 1024 and "8L/1024d/8h" in a["workload"]
+    assert bench.workload_config("large", 1024, 32, 0.1, 8)["grad_accum_per_rank"] == 4
+
+
+def test_gemm_dram_traffic_is_read_from_the_committed_capture(tmp_path, monkeypatch):
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    (prof / "r02_gemm_dram_bytes.csv").write_text(
+        "# comment\nmetric,bytes_per_launch\ndram__bytes_read.sum,200000000\ndram__bytes_write.sum,100000000\n")
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.read_gemm_dram_traffic() == 300000000.0
+    (prof / "r02_gemm_dram_bytes.csv").unlink()
+    assert bench.read_gemm_dram_traffic() is None
+
+
 def test_synthetic_batches_look_like_the_loaders_output():
     rng = np.random.RandomState(0)
     ids = bench.synth_ids(16, 1024, rng)
@@ -45,4 +73,6 @@ def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "mlm_train_tokens_per_s" and d["n_gpus"] == 2
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] > 0
+    assert d["steps"] == 1 and d["warmup"] == 0                       # the arm honours --steps / --warmup
+    assert d["config"] == bench.workload_config("small", 1024, 32, 0.1, 2)   # same config as the B200 arm
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
