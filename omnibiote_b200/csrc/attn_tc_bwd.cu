@@ -18,6 +18,7 @@
 // the compute warps in shared memory. Scalings (softmax scale, 1/(1-p)) are folded into the epilogues, which also
 // apply the rotary adjoint to dQ / dK. 12 warps: warpgroup 0 = TMA producer + MMA issuer (+ 2 idle), warpgroups
 // 1-2 = compute, with register reallocation between them (attn_tc_common.cuh).
+#include <stdlib.h>
 #include "attn_tc_common.cuh"
 
 namespace obt {
@@ -847,6 +848,20 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
 using namespace obt;
 
+// attn_tc_bwd16.cu
+int launch_attn_tc_dq16(const CUtensorMap& tm_qkv, const void* qkv, long long ld, const void* dy, long long lddy,
+                        const AttnTcParams& p, int C, dim3 grid, bool drop, cudaStream_t stream);
+int launch_attn_tc_dkv16(const CUtensorMap& tm_qkv, const CUtensorMap& tm_q64, const CUtensorMap& tm_dy64,
+                         const AttnTcParams& p, int C, dim3 grid, bool drop, cudaStream_t stream);
+
+// OBT_ATTN_BWD_WARPS=8|16 overrides the number of compute warps of the backward kernels (A/B runs)
+static int attn_bwd_compute_warps() {
+  const char* e = getenv("OBT_ATTN_BWD_WARPS");
+  if (e != nullptr && e[0] == '8') return 8;
+  if (e != nullptr && e[0] == '1' && e[1] == '6') return 16;
+  return 8;
+}
+
 extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, long long msb, long long msh,
                                long long msq, const int* row_lo, const int* row_hi, const void* y, long long ldy,
                                const void* dy, long long lddy, const float* lse, float* delta, void* dqkv, long long ldd,
@@ -913,14 +928,22 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
     attr_set = true;
   }
   dim3 grid((T + ATT_BM - 1) / ATT_BM, H, B);
-  if (drop_p > 0.f)
-    attn_tc_dq_kernel<true><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(
-        tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
-  else
-    attn_tc_dq_kernel<false><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(
-        tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
-  rc = check_launch("attn_tc_dq");
+  if (attn_bwd_compute_warps() == 16) {
+    rc = launch_attn_tc_dq16(tm_qkv, qkv, ld, dy, lddy, p, C, grid, drop_p > 0.f, stream);
+  } else {
+    if (drop_p > 0.f)
+      attn_tc_dq_kernel<true><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(
+          tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
+    else
+      attn_tc_dq_kernel<false><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(
+          tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
+    rc = check_launch("attn_tc_dq");
+  }
   if (rc) return rc;
+  // OBT_ATTN_DKV_WARPS overrides the dK/dV kernel alone (A/B runs)
+  int dkv_warps = attn_bwd_compute_warps();
+  if (const char* e = getenv("OBT_ATTN_DKV_WARPS")) dkv_warps = (e[0] == '1' && e[1] == '6') ? 16 : 8;
+  if (dkv_warps == 16) return launch_attn_tc_dkv16(tm_qkv, tm_q64, tm_dy64, p, C, grid, drop_p > 0.f, stream);
   if (drop_p > 0.f)
     attn_tc_dkv_kernel<true><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
   else

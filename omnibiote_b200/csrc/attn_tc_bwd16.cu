@@ -1,0 +1,827 @@
+// Attention backward, 16-compute-warp variants of the dQ and dK/dV kernels of attn_tc_bwd.cu (same math, same TMEM
+// and shared-memory layout, same barriers): four threads per TMEM lane with 16 score columns each instead of two with
+// 32. Why: the 8-warp kernels are latency-bound, not throughput-bound — per 64-key sub-tile the compute warps issue
+// ~2100 warp instructions (520 issue cycles per scheduler) and 512 cycles of MUFU against 768 cycles of MMA, yet a
+// sub-tile takes ~1700 cycles because each scheduler only has two compute warps and both sit in the same phase of the
+// wait -> tcgen05.ld -> exp -> tcgen05.st -> arrive sequence (issue slots 29-37 % busy, tensor pipe 34-41 %,
+// profiles/r01_attn_v8.details.txt). With 16 warps every scheduler interleaves four.
+// Selected by obt_attn_tc_bwd through OBT_ATTN_BWD_WARPS (attn_tc_bwd.cu).
+#include "attn_tc_common.cuh"
+
+namespace obt {
+
+constexpr int DQ16_KV_STAGES = 3;
+
+struct AttnDq16Smem {
+  static constexpr uint32_t K_OFF = 0;  // stages of 128 keys
+  static constexpr uint32_t V_OFF = K_OFF + DQ16_KV_STAGES * ATT_TILE_BYTES;
+  static constexpr uint32_t BAR_OFF = V_OFF + DQ16_KV_STAGES * ATT_TILE_BYTES;
+  static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
+};
+
+// TMEM: [0,128) / [128,256) score buffers S (64 columns) | dP (64 columns), ping-pong; [256,384) dQ accumulator;
+// [384,448) Q, [448,512) dO as packed bf16. Thread (quadrant q = warp & 3, column group cq = (warp - 4) >> 2) owns
+// S / dP columns [16 cq, 16 cq + 16) of TMEM lane 32 q + lane.
+template <bool kDrop>
+__global__ void __launch_bounds__(ATT_BWD16_THREADS, 1)
+attn_tc_dq16_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16* __restrict__ qkv, long long ld,
+                    const __nv_bfloat16* __restrict__ dy, long long lddy, const AttnTcParams p, int C) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  uint8_t* sK = smem + AttnDq16Smem::K_OFF;
+  uint8_t* sV = smem + AttnDq16Smem::V_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnDq16Smem::BAR_OFF);
+  uint64_t* qdo_ready = bars + 0;  // Q / dO are in TMEM (16 compute warps)
+  uint64_t* k_full = bars + 1;     // [3]
+  uint64_t* v_full = bars + 4;     // [3]
+  uint64_t* kv_empty = bars + 7;   // [3]
+  uint64_t* sdp_full = bars + 10;  // [2]
+  uint64_t* ds_full = bars + 12;   // [2]
+  uint64_t* dq_done = bars + 14;   // last dQ MMA completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  int* s_range = reinterpret_cast<int*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = blockIdx.x * ATT_BM;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int T = p.T;
+
+  // compute threads issue the global loads of their quarter rows of Q and dO first (d columns [32 cq, +32))
+  uint4 qv[4], dov[4];
+  {
+    const int r_ = (warp & 3) * 32 + lane, cq_ = (warp - ATT_BWD_FIRST_COMPUTE_WARP) >> 2;
+    const bool ok_ = warp >= ATT_BWD_FIRST_COMPUTE_WARP && t0 + r_ < T;
+    const long long row_ = static_cast<long long>(b) * T + t0 + r_;
+    const uint4* src = reinterpret_cast<const uint4*>(qkv + row_ * ld + h * ATT_D + (ok_ ? cq_ : 0) * 32);
+    const uint4* src2 = reinterpret_cast<const uint4*>(dy + row_ * lddy + h * ATT_D + (ok_ ? cq_ : 0) * 32);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      qv[g] = ok_ ? src[g] : make_uint4(0, 0, 0, 0);
+      dov[g] = ok_ ? src2[g] : make_uint4(0, 0, 0, 0);
+    }
+  }
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    mbar_init(qdo_ready, ATT_COMPUTE_WARPS16);
+    for (int i = 0; i < DQ16_KV_STAGES; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sdp_full[i], 1);
+      mbar_init(&ds_full[i], ATT_COMPUTE_WARPS16);
+    }
+    mbar_init(dq_done, 1);
+    fence_barrier_init();
+    s_range[0] = T;
+    s_range[1] = 0;
+    s_range[2] = 0;
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+  __syncthreads();
+  if (p.row_lo != nullptr && threadIdx.x < ATT_BM && t0 + static_cast<int>(threadIdx.x) < T) {
+    const int lo = p.row_lo[static_cast<long long>(b) * T + t0 + threadIdx.x];
+    const int hi = p.row_hi[static_cast<long long>(b) * T + t0 + threadIdx.x];
+    if (lo >= hi) {
+      atomicExch(&s_range[2], 1);
+    } else {
+      atomicMin(&s_range[0], lo);
+      atomicMax(&s_range[1], hi);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tmem_slot), 0);
+  auto tile_range = [&](int& jb_out, int& je_out) {
+    jb_out = 0;
+    je_out = (T + ATT_BN - 1) / ATT_BN;
+    if (p.row_lo != nullptr && s_range[2] == 0 && s_range[1] > s_range[0]) {
+      jb_out = s_range[0] / ATT_BN;
+      je_out = (s_range[1] + ATT_BN - 1) / ATT_BN;
+    }
+  };
+  const int row0 = b * T;
+  const int kcol = C + h * ATT_D, vcol = 2 * C + h * ATT_D;
+  constexpr uint32_t TM_DQ = 256, TM_Q = 384, TM_DO = 448;
+
+  if (warp < ATT_BWD_FIRST_COMPUTE_WARP) {
+    reg_dealloc<56>();
+    int jb, je;
+    tile_range(jb, je);
+    const int n_tiles = je - jb;    // 128-key tiles
+    const int n_sub = 2 * n_tiles;  // 64-key sub-tiles
+    if (warp == 0) {
+      if (lane == 0) {
+        int st = 0;
+        uint32_t ph = 0;
+        for (int jj = 0; jj < n_tiles; ++jj) {
+          const int krow = row0 + (jb + jj) * ATT_BN;
+          mbar_wait(&kv_empty[st], ph ^ 1);
+          mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
+          tma_load_2d(&tm_qkv, &k_full[st], sK + st * ATT_TILE_BYTES, kcol, krow);
+          tma_load_2d(&tm_qkv, &k_full[st], sK + st * ATT_TILE_BYTES + 16384, kcol + 64, krow);
+          mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
+          tma_load_2d(&tm_qkv, &v_full[st], sV + st * ATT_TILE_BYTES, vcol, krow);
+          tma_load_2d(&tm_qkv, &v_full[st], sV + st * ATT_TILE_BYTES + 16384, vcol + 64, krow);
+          if (++st == DQ16_KV_STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      const int n_sub_u = __shfl_sync(0xffffffffu, n_sub, 0);
+      const bool leader = elect_one();
+      mbar_wait(qdo_ready, 0);
+      auto issue_scores = [&](int s) {
+        const int jj = s >> 1, hsub = s & 1, st = jj % DQ16_KV_STAGES;
+        if (hsub == 0) {
+          const uint32_t ph = (jj / DQ16_KV_STAGES) & 1;
+          mbar_wait(&k_full[st], ph);
+          mbar_wait(&v_full[st], ph);
+        }
+        tc_fence_after();
+        if (leader) {
+          const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES) + hsub * 8192;
+          const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES) + hsub * 8192;
+          const uint32_t d = tmem_base + (s & 1) * 128;
+          issue_scores_ts_128x64(d, tmem_base + TM_Q, k_addr, 16384);        // S  = Q K^T
+          issue_scores_ts_128x64(d + 64, tmem_base + TM_DO, v_addr, 16384);  // dP = dO V^T
+          umma_commit(&sdp_full[s & 1]);
+        }
+        __syncwarp();
+      };
+      issue_scores(0);
+      for (int s = 0; s < n_sub_u; ++s) {
+        if (s + 1 < n_sub_u) issue_scores(s + 1);
+        const int jj = s >> 1, hsub = s & 1, st = jj % DQ16_KV_STAGES;
+        mbar_wait(&ds_full[s & 1], (s >> 1) & 1);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t k_rows = smem_u32(sK + st * ATT_TILE_BYTES) + hsub * 8192;
+          issue_grad_ts_128x128x64_q16(tmem_base + TM_DQ, tmem_base + (s & 1) * 128, k_rows, 16384, s > 0);  // dQ += dS K
+          if (hsub == 1) umma_commit(&kv_empty[st]);
+          if (s == n_sub_u - 1) umma_commit(dq_done);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    reg_alloc<112>();
+    int jb, je;
+    tile_range(jb, je);
+    const int n_sub = 2 * (je - jb);
+    const int q = warp & 3;
+    const int cq = (warp - ATT_BWD_FIRST_COMPUTE_WARP) >> 2;  // four threads per query row: columns [16 cq, +16)
+    const int r = q * 32 + lane;
+    const int i = t0 + r;
+    const bool row_ok = i < T;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    {  // Q and dO quarter rows -> TMEM (16 packed words each)
+      uint32_t w[16];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        w[g * 4 + 0] = qv[g].x; w[g * 4 + 1] = qv[g].y; w[g * 4 + 2] = qv[g].z; w[g * 4 + 3] = qv[g].w;
+      }
+      __syncwarp();
+      tmem_st_32x16(lane_addr + TM_Q + cq * 16, w);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        w[g * 4 + 0] = dov[g].x; w[g * 4 + 1] = dov[g].y; w[g * 4 + 2] = dov[g].z; w[g * 4 + 3] = dov[g].w;
+      }
+      tmem_st_32x16(lane_addr + TM_DO + cq * 16, w);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qdo_ready);
+    }
+    int lo = 0, hi = T;
+    float row_scale = p.scale;
+    if (p.row_lo != nullptr && row_ok) {
+      lo = p.row_lo[static_cast<long long>(b) * T + i];
+      hi = p.row_hi[static_cast<long long>(b) * T + i];
+      if (lo >= hi) { lo = 0; hi = T; row_scale = 0.f; }
+    }
+    const long long bh = static_cast<long long>(b) * p.H + h;
+    float off_nat = 0.f, ls2 = 0.f, dl = 0.f;
+    if (row_ok) {
+      off_nat = p.lse[2 * (bh * T + i)];
+      ls2 = p.lse[2 * (bh * T + i) + 1] * LOG2E;
+      dl = p.delta[bh * T + i];
+    }
+    const float neg = off_nat * LOG2E + ls2;
+    const float sc2 = row_scale * LOG2E;
+    const __nv_bfloat16* mrow =
+        (p.mask != nullptr && row_ok) ? p.mask + b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq : nullptr;
+    const float inv_keep = kDrop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    const float dlp = kDrop ? dl * (1.0f - p.drop_p) : dl;
+    const uint32_t* keep_row = nullptr;
+    if (kDrop && row_ok) keep_row = p.keep + (bh * T + i) * p.nw;
+    const int kw_shift = (cq & 1) * 4;  // keys 16..31 of a keep word: their bits sit 4 positions below keys 0..15
+
+    auto load_kw = [&](int s) -> uint32_t {
+      const int w = ((jb + (s >> 1)) * ATT_BN + (s & 1) * 64 + cq * 16) >> 5;
+      return (kDrop && keep_row != nullptr && s < n_sub && w < p.nw) ? keep_row[w] : 0xffffffffu;
+    };
+    uint32_t kw_next = load_kw(0);
+    for (int s = 0; s < n_sub; ++s) {
+      const int bsel = s & 1;
+      const int j0 = (jb + (s >> 1)) * ATT_BN + (s & 1) * 64 + cq * 16;  // first key of this thread's 16 columns
+      const uint32_t kw = kw_next << kw_shift;
+      kw_next = load_kw(s + 1);
+      mbar_wait(&sdp_full[bsel], (s >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[16], dv[16];
+      __syncwarp();
+      tmem_ld_32x16(lane_addr + bsel * 128 + cq * 16, sv);
+      tmem_ld_32x16(lane_addr + bsel * 128 + 64 + cq * 16, dv);
+      tmem_ld_wait();
+      float ds[16];
+      bool none_visible = false;
+      if (p.mask != nullptr) {  // dense additive bias (kernel-uniform branch)
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int j = j0 + e;
+          const bool vis = (j < T) && (mrow != nullptr);
+          const float bias = vis ? __bfloat162float(mrow[j]) : 0.f;
+          const float sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
+          ds[e] = vis ? fast_exp2((sp - off_nat) * LOG2E - ls2) : 0.f;
+        }
+      } else if (__all_sync(0xffffffffu, row_ok && j0 >= lo && j0 + 16 <= hi)) {
+        const float nneg = -neg;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) ds[e] = fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nneg));
+      } else {
+        const uint32_t vm = row_ok ? (interval_bits32(lo, hi, j0) & 0xffffu) : 0u;
+        if (__all_sync(0xffffffffu, vm == 0u)) {
+          none_visible = true;
+        } else {
+          const float nneg = -neg;
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            ds[e] = (vm & (1u << e)) ? fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nneg)) : 0.f;
+        }
+      }
+      if (none_visible) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) ds[e] = 0.f;
+      } else if (kDrop) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float dpk = (kw & (1u << keep_bit_pos(e))) ? __uint_as_float(dv[e]) : 0.f;
+          ds[e] *= dpk - dlp;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) ds[e] *= __uint_as_float(dv[e]) - dlp;
+      }
+      uint32_t pk[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(ds[2 * e], ds[2 * e + 1]);
+      __syncwarp();
+      tmem_st_32x8(lane_addr + bsel * 128 + cq * 16, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ds_full[bsel]);
+    }
+    // dQ epilogue: this thread stores d columns [32 cq, 32 cq + 32) of its row in two 16-column chunks
+    mbar_wait(dq_done, 0);
+    tc_fence_after();
+    __nv_bfloat16* drow = p.dq + (static_cast<long long>(row0) + i) * p.ldd + h * ATT_D;
+    const float oscale = row_scale * inv_keep;
+    const bool do_rope = row_ok && p.rope_cos != nullptr;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c16 = cq * 2 + cc;  // 16-column chunk index 0..7
+      uint32_t o[16];
+      __syncwarp();
+      tmem_ld_32x16(lane_addr + TM_DQ + c16 * 16, o);
+      tmem_ld_wait();
+      if (row_ok) {
+        float f[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(o[e]) * oscale;
+        if (do_rope) {
+          const long long toff = static_cast<long long>(i) * (ATT_D / 2) + c16 * 8;
+          float4 rcs[2], rsn[2];
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            rcs[g] = reinterpret_cast<const float4*>(p.rope_cos + toff)[g];
+            rsn[g] = p.rope_sin ? reinterpret_cast<const float4*>(p.rope_sin + toff)[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) f[e] = rb(f[e]);
+          rope_adjoint16(f, rcs, rsn, p.rope_sin != nullptr);
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          reinterpret_cast<uint4*>(drow + c16 * 16)[g] =
+              make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
+                         pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// =============================================================================================
+// dK / dV kernel, 16 compute warps: thread (quadrant q, column group cq) owns key row 32 q + lane and the S^T / dP^T
+// columns of queries [16 cq, 16 cq + 16) of the 64-query sub-tile; per-query parameters are staged per warp for its
+// 16 queries (lanes 16..31 mirror lanes 0..15 so that the warp votes see every query twice instead of garbage).
+//   TMEM  [0,128) / [128,256)  S^T (64 columns) | dP^T (64 columns), ping-pong;  [256,384) dV;  [384,512) dK
+// =============================================================================================
+constexpr uint32_t ATT_SUB16_BYTES = 64 * 128 * 2;  // one [64 rows x 128] bf16 tile = two 8 KB swizzle sub-tiles
+constexpr int ATT_QDO16_STAGES = 4;
+
+// per warp and buffer, for the warp's 16 queries: 16 x float2 {-(max+lsum)*log2e, delta*(1-p)} + 16 x int2 {lo,hi} +
+// 16 x float2 {max, lsum*log2e} + 16 x float live + 16 keep words + 16 visibility words
+constexpr uint32_t ATT_WPAR16_BYTES = 576;
+
+struct AttnDkv16Smem {
+  static constexpr uint32_t K_OFF = 0;
+  static constexpr uint32_t V_OFF = K_OFF + ATT_TILE_BYTES;
+  static constexpr uint32_t Q_OFF = V_OFF + ATT_TILE_BYTES;
+  static constexpr uint32_t DO_OFF = Q_OFF + ATT_QDO16_STAGES * ATT_SUB16_BYTES;
+  static constexpr uint32_t PAR_OFF = DO_OFF + ATT_QDO16_STAGES * ATT_SUB16_BYTES;  // [8 warps][2 buffers]
+  static constexpr uint32_t BAR_OFF = PAR_OFF + ATT_COMPUTE_WARPS16 * 2 * ATT_WPAR16_BYTES;
+  static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
+};
+
+template <bool kDrop>
+__global__ void __launch_bounds__(ATT_BWD16_THREADS, 1)
+attn_tc_dkv16_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_q64,
+                   const __grid_constant__ CUtensorMap tm_dy64, const AttnTcParams p, int C) {
+  // 1024-byte alignment (128B-swizzle atoms) is requested from the toolchain, so every smem address below is a
+  // link-time constant instead of a live register (the run-time round-up cost registers / spill reloads in the loops)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  uint8_t* sK = smem + AttnDkv16Smem::K_OFF;
+  uint8_t* sV = smem + AttnDkv16Smem::V_OFF;
+  uint8_t* sQ = smem + AttnDkv16Smem::Q_OFF;
+  uint8_t* sDO = smem + AttnDkv16Smem::DO_OFF;
+  uint8_t* sPar = smem + AttnDkv16Smem::PAR_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnDkv16Smem::BAR_OFF);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qdo_full = bars + 1;    // [4]
+  uint64_t* qdo_free = bars + 5;    // [4] dV/dK MMAs that read Q/dO stage s completed
+  uint64_t* sdp_full = bars + 9;    // [2]
+  uint64_t* pds_full = bars + 11;   // [2]
+  uint64_t* grads_done = bars + 13; // all dV/dK MMAs completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  unsigned int* s_rel = reinterpret_cast<unsigned int*>(bars + 15);  // relevance bits of the 64-query sub-tiles (<=128)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = blockIdx.x * ATT_BN;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int T = p.T;
+  const int nq = (T + 63) / 64;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_q64);
+    tma_prefetch_desc(&tm_dy64);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < ATT_QDO16_STAGES; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_free[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sdp_full[i], 1);
+      mbar_init(&pds_full[i], ATT_COMPUTE_WARPS16);
+    }
+    mbar_init(grads_done, 1);
+    fence_barrier_init();
+    s_rel[0] = s_rel[1] = s_rel[2] = s_rel[3] = 0;
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
+  __syncthreads();
+  const int row0 = b * T;
+  const int qcol = h * ATT_D, kcol = C + h * ATT_D, vcol = 2 * C + h * ATT_D;
+  if (warp == 0 && lane == 0) {  // K / V do not depend on the relevance scan below: get them in flight first
+    mbar_expect_tx(kv_full, 2 * ATT_TILE_BYTES);
+    tma_load_2d(&tm_qkv, kv_full, sK, kcol, row0 + j0);
+    tma_load_2d(&tm_qkv, kv_full, sK + 16384, kcol + 64, row0 + j0);
+    tma_load_2d(&tm_qkv, kv_full, sV, vcol, row0 + j0);
+    tma_load_2d(&tm_qkv, kv_full, sV + 16384, vcol + 64, row0 + j0);
+  }
+  // which 64-query sub-tiles can see this key tile at all
+  if (p.row_lo != nullptr) {
+    // four rows per thread and pass: all loads in flight before the first dependent atomic
+    for (int i0 = threadIdx.x; i0 < T; i0 += 4 * blockDim.x) {
+      int lo[4], hi[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        lo[u] = 1; hi[u] = 1;  // beyond T: an empty, irrelevant interval
+        if (i < T) {
+          lo[u] = p.row_lo[static_cast<long long>(b) * T + i];
+          hi[u] = p.row_hi[static_cast<long long>(b) * T + i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        const bool rel = i < T && ((lo[u] >= hi[u]) || (lo[u] < j0 + ATT_BN && hi[u] > j0));
+        if (rel) atomicOr(&s_rel[(i >> 6) >> 5], 1u << ((i >> 6) & 31));
+      }
+    }
+  } else if (threadIdx.x < 4) {
+    s_rel[threadIdx.x] = 0xffffffffu;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // shuffled from lane 0 so that the compiler knows the value is warp-uniform: tcgen05 operands then go through
+  // uniform registers directly instead of a per-lane R2UR waterfall loop around every MMA
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tmem_slot), 0);
+  // read from shared memory at every use: held in registers these words were live across the role split and got
+  // spilled, with the reloads on the compute loop's critical path
+  auto relevant = [&](int it) -> bool { return (s_rel[it >> 5] >> (it & 31)) & 1u; };
+
+  if (warp < ATT_BWD_FIRST_COMPUTE_WARP) {
+   reg_dealloc<56>();
+   if (warp == 0) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < nq; ++it) {
+        if (!relevant(it)) continue;
+        mbar_wait(&qdo_free[st], ph ^ 1);
+        mbar_expect_tx(&qdo_full[st], 2 * ATT_SUB16_BYTES);
+        const int qrow = row0 + it * 64;
+        tma_load_2d(&tm_q64, &qdo_full[st], sQ + st * ATT_SUB16_BYTES, qcol, qrow);
+        tma_load_2d(&tm_q64, &qdo_full[st], sQ + st * ATT_SUB16_BYTES + 8192, qcol + 64, qrow);
+        tma_load_2d(&tm_dy64, &qdo_full[st], sDO + st * ATT_SUB16_BYTES, qcol, qrow);
+        tma_load_2d(&tm_dy64, &qdo_full[st], sDO + st * ATT_SUB16_BYTES + 8192, qcol + 64, qrow);
+        if (++st == ATT_QDO16_STAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // whole warp in the uniform control flow, one elected issuer (see the dQ kernel)
+    const bool leader = elect_one();
+    const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+    int n_total = 0;
+    for (int it = 0; it < nq; ++it) n_total += relevant(it) ? 1 : 0;
+    n_total = __shfl_sync(0xffffffffu, n_total, 0);
+    mbar_wait(kv_full, 0);
+    auto issue_scores = [&](int n) {  // Q/dO stage n % 4, TMEM score buffer n & 1
+      const int st = n % ATT_QDO16_STAGES, tb = n & 1;
+      mbar_wait(&qdo_full[st], (n / ATT_QDO16_STAGES) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t d = tmem_base + tb * 128;
+        issue_scores_128x64(d, k_addr, 16384, smem_u32(sQ + st * ATT_SUB16_BYTES), 8192);        // S^T  = K Q^T
+        issue_scores_128x64(d + 64, v_addr, 16384, smem_u32(sDO + st * ATT_SUB16_BYTES), 8192);  // dP^T = V dO^T
+        umma_commit(&sdp_full[tb]);
+      }
+      __syncwarp();
+    };
+    if (n_total > 0) issue_scores(0);
+    for (int n = 0; n < n_total; ++n) {
+      // the scores of n+1 overwrite the buffer the gradient products of n-1 read from: MMAs execute in issue order
+      if (n + 1 < n_total) issue_scores(n + 1);
+      const int st = n % ATT_QDO16_STAGES, tb = n & 1;
+      mbar_wait(&pds_full[tb], (n >> 1) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t buf = tmem_base + tb * 128;
+        issue_grad_ts_128x128x64_q16(tmem_base + 256, buf, smem_u32(sDO + st * ATT_SUB16_BYTES), 8192, n > 0);      // dV += P^T dO
+        issue_grad_ts_128x128x64_q16(tmem_base + 384, buf + 64, smem_u32(sQ + st * ATT_SUB16_BYTES), 8192, n > 0);  // dK += dS^T Q
+        umma_commit(&qdo_free[st]);
+        if (n == n_total - 1) umma_commit(grads_done);
+      }
+      __syncwarp();
+    }
+   }
+  } else {
+    reg_alloc<112>();
+    const int q = warp & 3;
+    const int cq = (warp - ATT_BWD_FIRST_COMPUTE_WARP) >> 2;  // four threads per key row: query columns [16*cq, +16)
+    const int lq = lane & 15;  // query slot of this lane in the warp's parameter tables (lanes 16..31 mirror 0..15)
+    const int r = q * 32 + lane;     // key row within the tile
+    const int j = j0 + r;
+    const bool key_ok = j < T;
+    const int kq0 = j0 + q * 32;     // first key of this warp
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const long long bh = static_cast<long long>(b) * p.H + h;
+    const float inv_keep = kDrop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    const float keep_frac = kDrop ? 1.0f - p.drop_p : 1.0f;
+    const float sc2 = p.scale * LOG2E;
+    const uint32_t mybit = 1u << keep_bit_pos(lane);  // this key's bit inside the keep word of its 32-key group
+    uint8_t* wpar = sPar + (warp - ATT_BWD_FIRST_COMPUTE_WARP) * 2 * ATT_WPAR16_BYTES;
+    // Per-query parameters of THIS warp's 32 query columns (lane = query), software-pipelined: the global loads for
+    // the next relevant sub-tile are issued before the math of the current one and staged in the warp's other smem
+    // buffer afterwards; the math reads them back as warp-wide broadcasts.
+    // load_params only ISSUES the global loads (raw values; no arithmetic or branches on loaded data, which would
+    // stall the in-order warp right there); finish_params turns them into the staged form after the math.
+    struct QParams { int lo, hi; float off, ls2, dl, live; uint32_t kw, vm; };
+    auto load_params = [&](int it) -> QParams {
+      QParams z;
+      z.lo = 0; z.hi = 0; z.off = 0.f; z.ls2 = 0.f; z.dl = 0.f; z.live = 1.f;  // query beyond T: contributes nothing
+      z.kw = 0xffffffffu;
+      z.vm = 0u;
+      const int i = it * 64 + cq * 16 + lq;
+      if (i < T) {
+        z.hi = T;
+        if (p.row_lo != nullptr) {
+          z.lo = p.row_lo[static_cast<long long>(b) * T + i];
+          z.hi = p.row_hi[static_cast<long long>(b) * T + i];
+        }
+        const float2 ml = *reinterpret_cast<const float2*>(p.lse + 2 * (bh * T + i));
+        z.off = ml.x;
+        z.ls2 = ml.y;
+        z.dl = p.delta[bh * T + i];
+        if (kDrop && (kq0 >> 5) < p.nw) z.kw = p.keep[(bh * T + i) * p.nw + (kq0 >> 5)];
+      }
+      return z;
+    };
+    auto finish_params = [&](QParams& z, int it) {
+      const int i = it * 64 + cq * 16 + lq;
+      if (i < T) {
+        if (z.lo >= z.hi) { z.lo = 0; z.hi = T; z.live = 0.f; }  // fully-masked row: uniform P, no dS
+        z.vm = interval_bits32(z.lo, z.hi, kq0);  // hi <= T: keys beyond the sequence are never visible
+      }
+      z.ls2 *= LOG2E;
+      z.dl *= keep_frac;
+    };
+    auto store_params = [&](int buf, const QParams& z) {
+      uint8_t* base = wpar + buf * ATT_WPAR16_BYTES;
+      if (lane < 16) {
+        reinterpret_cast<float2*>(base)[lq] = make_float2(-(z.off * LOG2E + z.ls2), z.dl);
+        reinterpret_cast<int2*>(base + 128)[lq] = make_int2(z.lo, z.hi);
+        reinterpret_cast<float2*>(base + 256)[lq] = make_float2(z.off, z.ls2);
+        reinterpret_cast<float*>(base + 384)[lq] = z.live;
+        reinterpret_cast<uint32_t*>(base + 448)[lq] = z.kw;
+        reinterpret_cast<uint32_t*>(base + 512)[lq] = z.vm;
+      }
+    };
+    auto next_relevant = [&](int it) -> int {
+      ++it;
+      while (it < nq && !relevant(it)) ++it;
+      return it;
+    };
+
+    // two sub-tiles of look-ahead: the keep words come from HBM (written a whole forward pass earlier) and one
+    // sub-tile of math (~1 us) did not cover that latency (11 % of the stall samples sat on the first use)
+    int n = 0;
+    int it = next_relevant(-1);
+    int nx = it < nq ? next_relevant(it) : nq;
+    QParams cur = {}, zn = {};
+    if (it < nq) {
+      cur = load_params(it);
+      if (nx < nq) zn = load_params(nx);
+      finish_params(cur, it);
+      store_params(0, cur);
+    }
+    __syncwarp();
+    while (it < nq) {
+      const int st = n & 1;
+      const int i0 = it * 64 + cq * 16;
+      const int nx2 = nx < nq ? next_relevant(nx) : nq;
+      QParams zn2 = {};
+      if (nx2 < nq) zn2 = load_params(nx2);  // in flight during the math of this AND the next sub-tile
+      const uint8_t* base = wpar + st * ATT_WPAR16_BYTES;
+      const float4* nd4 = reinterpret_cast<const float4*>(base);            // two queries per float4
+      const int2* c_lh = reinterpret_cast<const int2*>(base + 128);
+      const float2* c_x = reinterpret_cast<const float2*>(base + 256);
+      const float* c_live = reinterpret_cast<const float*>(base + 384);
+      const uint4* kp4 = reinterpret_cast<const uint4*>(base + 448);        // four queries per uint4
+      const uint4* vp4 = reinterpret_cast<const uint4*>(base + 512);
+      const uint32_t lanebit = 1u << lane;
+      // every key of this warp visible to every (live) query of its 32 columns: one vote
+      const bool interior = (p.mask == nullptr) && (kq0 + 32 <= T) &&
+                            __all_sync(0xffffffffu, cur.live != 0.f && cur.lo <= kq0 && cur.hi >= kq0 + 32);
+      mbar_wait(&sdp_full[st], (n >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[16], dv[16];
+      __syncwarp();
+      tmem_ld_32x16(lane_addr + st * 128 + cq * 16, sv);
+      tmem_ld_32x16(lane_addr + st * 128 + 64 + cq * 16, dv);
+      tmem_ld_wait();
+      uint32_t ptw[8], dsw[8];  // bf16 pairs of P^T and dS^T
+      if (interior) {
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) {
+          uint4 kk = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+          if (kDrop) kk = kp4[e4];
+          const uint32_t kws[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const float4 nd = nd4[e4 * 2 + h2];
+            const int e = e4 * 4 + h2 * 2;
+            const float pr0 = fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nd.x));
+            const float pr1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), sc2, nd.z));
+            const bool kb0 = !kDrop || (kws[h2 * 2] & mybit), kb1 = !kDrop || (kws[h2 * 2 + 1] & mybit);
+            ptw[e >> 1] = pack_bf16x2(kb0 ? pr0 : 0.f, kb1 ? pr1 : 0.f);
+            dsw[e >> 1] = pack_bf16x2(pr0 * ((kb0 ? __uint_as_float(dv[e]) : 0.f) - nd.y),
+                                      pr1 * ((kb1 ? __uint_as_float(dv[e + 1]) : 0.f) - nd.w));
+          }
+        }
+      } else if (p.mask == nullptr && __all_sync(0xffffffffu, cur.vm == 0u && cur.live != 0.f)) {
+        // no query of the chunk sees any key of this warp: P^T = dS^T = 0, no exponentials
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ptw[e] = dsw[e] = 0u;
+      } else if (p.mask == nullptr && __all_sync(0xffffffffu, cur.live != 0.f)) {
+        // an interval end crosses the 32 x 32 block: per-query visibility words, one bit test per element
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) {
+          uint4 kk = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+          if (kDrop) kk = kp4[e4];
+          const uint4 vv = vp4[e4];
+          const uint32_t kws[4] = {kk.x, kk.y, kk.z, kk.w};
+          const uint32_t vms[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const float4 nd = nd4[e4 * 2 + h2];
+            const int e = e4 * 4 + h2 * 2;
+            const float pr0 = (vms[h2 * 2] & lanebit) ? fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nd.x)) : 0.f;
+            const float pr1 = (vms[h2 * 2 + 1] & lanebit) ? fast_exp2(fmaf(__uint_as_float(sv[e + 1]), sc2, nd.z)) : 0.f;
+            const bool kb0 = !kDrop || (kws[h2 * 2] & mybit), kb1 = !kDrop || (kws[h2 * 2 + 1] & mybit);
+            ptw[e >> 1] = pack_bf16x2(kb0 ? pr0 : 0.f, kb1 ? pr1 : 0.f);
+            dsw[e >> 1] = pack_bf16x2(pr0 * ((kb0 ? __uint_as_float(dv[e]) : 0.f) - nd.y),
+                                      pr1 * ((kb1 ? __uint_as_float(dv[e + 1]) : 0.f) - nd.w));
+          }
+        }
+      } else if (p.mask == nullptr) {
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) {
+          uint4 kk = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+          if (kDrop) kk = kp4[e4];
+          const uint32_t kws[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            float prs[2], dss[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int e = e4 * 4 + h2 * 2 + u;
+              const float2 nd = reinterpret_cast<const float2*>(nd4)[e];
+              const int2 lh = c_lh[e];
+              const float live = c_live[e];
+              const bool vis = key_ok && j >= lh.x && j < lh.y;
+              const float pr = vis ? fast_exp2(fmaf(__uint_as_float(sv[e]) * live, sc2, nd.x)) : 0.f;
+              const bool kb = !kDrop || (kws[h2 * 2 + u] & mybit);
+              prs[u] = kb ? pr : 0.f;
+              dss[u] = pr * ((kb ? __uint_as_float(dv[e]) : 0.f) - nd.y) * live;
+            }
+            ptw[e4 * 2 + h2] = pack_bf16x2(prs[0], prs[1]);
+            dsw[e4 * 2 + h2] = pack_bf16x2(dss[0], dss[1]);
+          }
+        }
+      } else {  // dense additive bias
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) {
+          uint4 kk = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+          if (kDrop) kk = kp4[e4];
+          const uint32_t kws[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            float prs[2], dss[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int e = e4 * 4 + h2 * 2 + u;
+              const int i = i0 + e;
+              const float2 nd = reinterpret_cast<const float2*>(nd4)[e];
+              const float2 cx = c_x[e];
+              const bool vis = key_ok && i < T;
+              const float bias =
+                  vis ? __bfloat162float(p.mask[b * p.msb + h * p.msh + static_cast<long long>(i) * p.msq + j]) : 0.f;
+              const float sp = __fadd_rn(__fmul_rn(__uint_as_float(sv[e]), p.scale), bias);
+              const float pr = vis ? fast_exp2((sp - cx.x) * LOG2E - cx.y) : 0.f;
+              const bool kb = !kDrop || (kws[h2 * 2 + u] & mybit);
+              prs[u] = kb ? pr : 0.f;
+              dss[u] = pr * ((kb ? __uint_as_float(dv[e]) : 0.f) - nd.y);
+            }
+            ptw[e4 * 2 + h2] = pack_bf16x2(prs[0], prs[1]);
+            dsw[e4 * 2 + h2] = pack_bf16x2(dss[0], dss[1]);
+          }
+        }
+      }
+      // P^T over the first 16 of the S^T columns this thread has read, dS^T over the first 16 of its dP^T columns
+      __syncwarp();
+      tmem_st_32x8(lane_addr + st * 128 + cq * 16, ptw);
+      tmem_st_32x8(lane_addr + st * 128 + 64 + cq * 16, dsw);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pds_full[st]);
+      // parameters of the next sub-tile into the warp's other buffer (last read during sub-tile n-1)
+      if (nx < nq) {
+        finish_params(zn, nx);
+        store_params(st ^ 1, zn);
+      }
+      cur = zn;
+      zn = zn2;
+      __syncwarp();
+      it = nx;
+      nx = nx2;
+      ++n;
+    }
+    // epilogue: four threads per key row, 64 of the 256 accumulator columns each (cq 0,1: dV / (1-p); cq 2,3:
+    // dK * scale / (1-p) with the rotary adjoint), in 16-column chunks
+    const bool is_dk = cq >= 2;
+    __nv_bfloat16* orow = (is_dk ? p.dk : p.dv) + (static_cast<long long>(row0) + j) * p.ldd + h * ATT_D + (cq & 1) * 64;
+    const float oscale = is_dk ? inv_keep * p.scale : inv_keep;
+    const bool do_rope = is_dk && key_ok && p.rope_cos != nullptr;
+    if (n > 0) {
+      mbar_wait(grads_done, 0);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t o[16];
+      __syncwarp();
+      if (n > 0) {
+        tmem_ld_32x16(lane_addr + 256 + cq * 64 + cc * 16, o);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o[e] = 0u;
+      }
+      if (key_ok) {
+        float f[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(o[e]) * oscale;
+        if (do_rope) {  // dK: adjoint of the rotary embedding at key position j
+          const long long toff = static_cast<long long>(j) * (ATT_D / 2) + (cq & 1) * 32 + cc * 8;
+          float4 rcs[2], rsn[2];
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            rcs[g] = reinterpret_cast<const float4*>(p.rope_cos + toff)[g];
+            rsn[g] = p.rope_sin ? reinterpret_cast<const float4*>(p.rope_sin + toff)[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) f[e] = rb(f[e]);
+          rope_adjoint16(f, rcs, rsn, p.rope_sin != nullptr);
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          reinterpret_cast<uint4*>(orow + cc * 16)[g] =
+              make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
+                         pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+}  // namespace obt
+
+using namespace obt;
+
+// launched by obt_attn_tc_bwd (attn_tc_bwd.cu)
+int launch_attn_tc_dq16(const CUtensorMap& tm_qkv, const void* qkv, long long ld, const void* dy, long long lddy,
+                        const AttnTcParams& p, int C, dim3 grid, bool drop, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(attn_tc_dq16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          AttnDq16Smem::BYTES);
+    cudaError_t e2 = cudaFuncSetAttribute(attn_tc_dq16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          AttnDq16Smem::BYTES);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      set_last_error("obt_attn_tc_bwd: cudaFuncSetAttribute(dq16): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      return OBT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  if (drop)
+    attn_tc_dq16_kernel<true><<<grid, ATT_BWD16_THREADS, AttnDq16Smem::BYTES, stream>>>(
+        tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
+  else
+    attn_tc_dq16_kernel<false><<<grid, ATT_BWD16_THREADS, AttnDq16Smem::BYTES, stream>>>(
+        tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
+  return check_launch("attn_tc_dq16");
+}
+
+int launch_attn_tc_dkv16(const CUtensorMap& tm_qkv, const CUtensorMap& tm_q64, const CUtensorMap& tm_dy64,
+                         const AttnTcParams& p, int C, dim3 grid, bool drop, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(attn_tc_dkv16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          AttnDkv16Smem::BYTES);
+    cudaError_t e2 = cudaFuncSetAttribute(attn_tc_dkv16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          AttnDkv16Smem::BYTES);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      set_last_error("obt_attn_tc_bwd: cudaFuncSetAttribute(dkv16): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      return OBT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  if (drop)
+    attn_tc_dkv16_kernel<true><<<grid, ATT_BWD16_THREADS, AttnDkv16Smem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
+  else
+    attn_tc_dkv16_kernel<false><<<grid, ATT_BWD16_THREADS, AttnDkv16Smem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
+  return check_launch("attn_tc_dkv16");
+}

@@ -118,6 +118,42 @@ __device__ __forceinline__ void issue_grad_ts_128x128x64(uint32_t d_tmem, uint32
   }
 }
 
+// Same with A written as FOUR 8-column pieces, one per K-step of 16 reduction indices, 16 columns apart (the
+// 16-compute-warp kernels: four threads per TMEM lane, each owning 16 score columns and writing its 8 packed words
+// over the first 8 of them).
+__device__ __forceinline__ void issue_grad_ts_128x128x64_q16(uint32_t d_tmem, uint32_t a_base, uint32_t b_addr,
+                                                             uint32_t b_lbo, bool accumulate) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, true);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const uint64_t b_desc = make_smem_desc_sw128(b_addr + kk * 2048, b_lbo, 1024);
+    umma_bf16_ts(d_tmem, a_base + kk * 16, b_desc, idesc, (accumulate || kk > 0) ? 1u : 0u);
+  }
+}
+
+// adjoint rotary on 16 consecutive d-columns (8 pairs): cs / sn = the 8 table entries (2 x float4)
+__device__ __forceinline__ void rope_adjoint16(float (&f)[16], const float4* cs, const float4* sn, bool has_sin) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const float c[4] = {cs[g].x, cs[g].y, cs[g].z, cs[g].w};
+    if (has_sin) {
+      const float s4[4] = {sn[g].x, sn[g].y, sn[g].z, sn[g].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = f[g * 8 + 2 * j], b = f[g * 8 + 2 * j + 1];
+        f[g * 8 + 2 * j] = a * c[j] + b * s4[j];
+        f[g * 8 + 2 * j + 1] = b * c[j] - a * s4[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f[g * 8 + 2 * j] *= c[j];
+        f[g * 8 + 2 * j + 1] *= c[j];
+      }
+    }
+  }
+}
+
 // bit k set <=> position base + k lies in [lo, hi), k = 0..31
 __device__ __forceinline__ uint32_t interval_bits32(int lo, int hi, int base) {
   const int a = min(max(lo - base, 0), 32), b = min(max(hi - base, 0), 32);
@@ -133,5 +169,12 @@ constexpr int ATT_COMPUTE_WARPS = 8;
 // spilled in the compute loops and reloaded the spills on the critical path (profiles/r01_attn_v7_bwd.source.txt).
 constexpr int ATT_BWD_THREADS = 384;
 constexpr int ATT_BWD_FIRST_COMPUTE_WARP = 4;
+// 16-compute-warp variants (attn_tc_bwd16.cu): 20 warps, four threads per TMEM lane with 16 score columns each. The
+// 8-warp kernels are latency-bound (issue slots 29-37 % busy with 2 compute warps per scheduler, all in the same
+// phase of the load / exp / store sequence: profiles/r01_attn_v8.details.txt); twice the warps with half the columns
+// keep the same instruction count and give every scheduler four warps to interleave. 96 registers per thread at
+// launch (65536 / 640), the producer warpgroup drops to 56, the compute warpgroups take 112.
+constexpr int ATT_COMPUTE_WARPS16 = 16;
+constexpr int ATT_BWD16_THREADS = 128 + 32 * ATT_COMPUTE_WARPS16;
 
 }  // namespace obt

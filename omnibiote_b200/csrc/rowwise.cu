@@ -345,20 +345,19 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
   }
   __syncthreads();
   {
-    // 256 threads = 32 columns x 8 row groups; 128-byte coalesced reads per partial row
-    float* red = s_dg;  // reuse: [8][33]
-    const int tx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    // 32 columns x (blockDim.x / 32) row groups; 128-byte coalesced reads per partial row
+    float* red = s_dg;  // reuse: [nry][33]
+    const int tx = threadIdx.x & 31, ry = threadIdx.x >> 5, nry = blockDim.x >> 5;
     const int col = blockIdx.x * 32 + tx;
     float t = 0.f;
-    if (col < C && ry < 8)
-      for (int bk = ry; bk < static_cast<int>(gridDim.x); bk += 8)
+    if (col < C)
+      for (int bk = ry; bk < static_cast<int>(gridDim.x); bk += nry)
         t += __ldcg(dgamma_partial + static_cast<long long>(bk) * C + col);
-    if (ry < 8) red[ry * 33 + tx] = t;
+    red[ry * 33 + tx] = t;
     __syncthreads();
     if (ry == 0 && col < C) {
       float tot = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) tot += red[k * 33 + tx];
+      for (int k = 0; k < nry; ++k) tot += red[k * 33 + tx];
       float o = rb(tot);
       if (accumulate_dgamma) o += __bfloat162float(dgamma[col]);
       dgamma[col] = __float2bfloat16_rn(o);
@@ -599,15 +598,33 @@ extern "C" int obt_layernorm_bwd(const void* dy, const void* x, const void* gamm
   OBT_REQUIRE(M > 0, "obt_layernorm_bwd: empty input");
   OBT_REQUIRE(dx_drop == nullptr || (drop_p > 0.f && drop_p < 1.f), "obt_layernorm_bwd: drop_p=%f with dx_drop", drop_p);
   const int wpb = (C <= 1024) ? 8 : 4;  // 32 KB of dgamma staging per block either way
+  const size_t smem_bytes = static_cast<size_t>(wpb) * ((C <= 1024) ? 4 : 8) * 256 * sizeof(float);
   const int max_grid = sm_count() * 4;
-  int grid = max_grid;
+  // ONE wave: every block must be resident at once. The reducer blocks of the fused dgamma tail hold their slot while
+  // they wait for the last partial; with more blocks than slots (592 on 296) those 32 held slots pushed the remaining
+  // blocks into a third wave (59.7 -> 105.9 us, profiles/r02a_launches.txt). The row loop is grid-strided anyway.
+  static int occ4 = 0, occ8 = 0;
+  int& occ = (C <= 1024) ? occ4 : occ8;
+  if (occ == 0) {
+    cudaError_t e = (C <= 1024)
+        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bwd_kernel<4>, wpb * 32, smem_bytes)
+        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bwd_kernel<8>, wpb * 32, smem_bytes);
+    if (e != cudaSuccess || occ < 1) {
+      occ = 0;
+      set_last_error("obt_layernorm_bwd: occupancy query failed: %s", cudaGetErrorString(e));
+      return OBT_ERR_CUDA;
+    }
+  }
+  int grid = sm_count() * occ;
+  if (grid > max_grid) grid = max_grid;
   if (M < static_cast<long long>(grid) * wpb) grid = static_cast<int>((M + wpb - 1) / wpb);
   if (grid < 1) grid = 1;
   // the reducer blocks (the first ceil(C/32)) must exist: with very few rows the grid is padded (row loop is a no-op)
   const int n_reducers = (C + 31) / 32;
   if (grid < n_reducers) grid = n_reducers;
-  OBT_REQUIRE(grid <= max_grid, "obt_layernorm_bwd: C=%d needs more reducer blocks than the workspace has rows", C);
-  const size_t smem = static_cast<size_t>(wpb) * ((C <= 1024) ? 4 : 8) * 256 * sizeof(float);
+  OBT_REQUIRE(grid <= max_grid && grid <= sm_count() * occ,
+              "obt_layernorm_bwd: C=%d needs more reducer blocks than can be resident", C);
+  const size_t smem = smem_bytes;
   auto a = static_cast<const __nv_bfloat16*>(dy);
   auto b = static_cast<const __nv_bfloat16*>(x);
   auto g = static_cast<const __nv_bfloat16*>(gamma);

@@ -9,6 +9,13 @@ pytestmark = pytest.mark.gpu
 BF = torch.bfloat16
 
 
+@pytest.fixture(autouse=True, params=[8, 16], ids=["bwd8warps", "bwd16warps"])
+def _backward_variant(request, monkeypatch):
+    """every test of this module runs with both layouts of the backward kernels (8 / 16 compute warps)"""
+    monkeypatch.setenv("OBT_ATTN_BWD_WARPS", str(request.param))
+    yield
+
+
 def _ref(qkv, B, T, H, d, scale, mask4):
     C = H * d
     q, k, v = [t.view(B, T, H, d).transpose(1, 2).float() for t in qkv.float().split(C, dim=1)]
