@@ -7,7 +7,8 @@
 //   warp 0      : TMA producer  - cp.async.bulk.tensor tiles into a 128B-swizzled smem ring (mbarrier full/empty)
 //   warp 1      : MMA issuer    - one thread issues tcgen05.mma (128|256 x 256 x 16), accumulators in TMEM,
 //                                 2 accumulator stages (2 x 256 columns) so the epilogue overlaps the next tile
-//   warps 2..5  : epilogue      - tcgen05.ld (row per thread) -> fused epilogue -> vectorised global stores
+//   warps 2..9  : epilogue      - 8 warps, two per TMEM lane quadrant (128 columns each): tcgen05.ld (row per thread)
+//                                 -> swizzled smem transpose -> fused epilogue -> coalesced 16-byte global stores
 // Operand layouts: either operand may be K-major (K contiguous in memory) or MN-major (M/N contiguous), which covers
 // forward (K,K), dgrad (K,MN) and wgrad (MN,MN) without materialising transposes.
 #include "common.cuh"
