@@ -41,6 +41,9 @@ void obt_clear_descriptor_cache(void);
  *           5 D = rb(aux_in + dropout(rb(acc)))        resid_dropout + residual (model.py:151,167,179-180)
  *           9 aux_out = rb(gelu'(U)), D = rb(gelu(U)) with U = rb(acc): forward of fused_gelu that saves the DERIVATIVE
  *          10 D = rb(rb(acc) * aux_in): its backward (aux_in = the saved derivative); 9 + 10 replace 2 + 3 in the block
+ *          11 D = rb(acc) and workspace[b, h, t] (fp32 [M / rope_T, N / 128, rope_T]) = sum over the 128 columns of
+ *             head h of D * aux_in: the attention backward's delta = rowsum(dO * O) emitted by the GEMM that produces
+ *             dO = d_a Wo (aux_in = y of model.py:148; rope_T = sequence length; N %% 128 == 0)
  *           8 D = aux_in[row] ? rb(acc) : 0 with aux_in a uint8 row mask [M]: MLM head whose unmasked rows are never
  *             read (zero loss weight and gradient, train_encoder.py:301-305); pairs with obt_ce_bwd(unmasked_rows_zero)
  *           7 D = rb(rotary(rb(acc))) on columns < rope_cols: apply_rotary_emb (model.py:39-50,108) fused into
@@ -128,14 +131,17 @@ int obt_attn_tc_fwd(const void* qkv, long long ld, const void* mask, long long m
                     float scale, float drop_p, const unsigned int* keep, cudaStream_t stream);
 
 /* tensor-core backward (head_dim == 128): delta pre-pass + dQ kernel + dK/dV kernel. dqkv is the fused [M,3C]
- * gradient buffer (dq | dk | dv, pitch ldd); delta is fp32 [B,H,T] scratch; autograd adjoint of model.py:111-148.
+ * gradient buffer (dq | dk | dv, pitch ldd); delta is fp32 [B,H,T]: scratch written by the pre-pass, or, with
+ * delta_ready != 0, an INPUT already holding rowsum(dy * y) per head (obt_gemm_bf16 epilogue 11 emits it while
+ * producing dy, and the pre-pass is skipped); autograd adjoint of model.py:111-148.
+ * OBT_ATTN_BWD_WARPS / OBT_ATTN_DKV_WARPS = 8 | 16 (environment) select the compute-warp layout of the kernels.
  * rope_cos / rope_sin (optional, fp32 [>=T, 64]): when given, the adjoint of apply_rotary_emb is applied to dq and dk
  * in the kernels' epilogues (rope_sin = NULL: cosine scaling), so dqkv is the gradient of the PRE-rotary c_attn output. */
 int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, long long msb, long long msh, long long msq,
                     const int* row_lo, const int* row_hi, const void* y, long long ldy, const void* dy, long long lddy,
-                    const float* lse, float* delta, void* dqkv, long long ldd, int B, int H, int T, int d, float scale,
-                    float drop_p, const unsigned int* keep, const float* rope_cos, const float* rope_sin,
-                    cudaStream_t stream);
+                    const float* lse, float* delta, int delta_ready, void* dqkv, long long ldd, int B, int H, int T,
+                    int d, float scale, float drop_p, const unsigned int* keep, const float* rope_cos,
+                    const float* rope_sin, cudaStream_t stream);
 
 /* ---- attention-mask producers / compressors (input contract of the hot path) ------------------------------------
  * obt_doc_mask_intervals : per (b,i) visible key interval [lo,hi) from token ids = create_attention_mask

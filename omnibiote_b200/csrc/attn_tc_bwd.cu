@@ -864,9 +864,10 @@ static int attn_bwd_compute_warps() {
 
 extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, long long msb, long long msh,
                                long long msq, const int* row_lo, const int* row_hi, const void* y, long long ldy,
-                               const void* dy, long long lddy, const float* lse, float* delta, void* dqkv, long long ldd,
-                               int B, int H, int T, int d, float scale, float drop_p, const unsigned int* keep,
-                               const float* rope_cos, const float* rope_sin, cudaStream_t stream) {
+                               const void* dy, long long lddy, const float* lse, float* delta, int delta_ready,
+                               void* dqkv, long long ldd, int B, int H, int T, int d, float scale, float drop_p,
+                               const unsigned int* keep, const float* rope_cos, const float* rope_sin,
+                               cudaStream_t stream) {
   OBT_REQUIRE(qkv && y && dy && lse && delta && dqkv, "obt_attn_tc_bwd: null pointer");
   OBT_REQUIRE((reinterpret_cast<uintptr_t>(rope_cos) & 15) == 0 && (reinterpret_cast<uintptr_t>(rope_sin) & 15) == 0,
               "obt_attn_tc_bwd: rotary tables must be 16-byte aligned");
@@ -890,7 +891,7 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
   rc = get_tensor_map_2d(&tm_dy64, dy, static_cast<uint64_t>(C), static_cast<uint64_t>(M), static_cast<uint64_t>(lddy), 64,
                          64);
   if (rc) return rc;
-  {
+  if (!delta_ready) {  // otherwise the GEMM that produced dy already emitted delta (epilogue 11)
     const int warps = 8;
     attn_delta_kernel<<<static_cast<unsigned>((M + warps - 1) / warps), warps * 32, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(dy), lddy, static_cast<const __nv_bfloat16*>(y), ldy, delta, B, H, T);

@@ -168,7 +168,7 @@ attn_tc_dq16_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
       }
     }
   } else {
-    reg_alloc<112>();
+    reg_alloc<104>();
     int jb, je;
     tile_range(jb, je);
     const int n_sub = 2 * (je - jb);
@@ -502,7 +502,7 @@ attn_tc_dkv16_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     }
    }
   } else {
-    reg_alloc<112>();
+    reg_alloc<104>();
     const int q = warp & 3;
     const int cq = (warp - ATT_BWD_FIRST_COMPUTE_WARP) >> 2;  // four threads per key row: query columns [16*cq, +16)
     const int lq = lane & 15;  // query slot of this lane in the warp's parameter tables (lanes 16..31 mirror 0..15)

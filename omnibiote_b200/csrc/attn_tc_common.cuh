@@ -172,8 +172,10 @@ constexpr int ATT_BWD_FIRST_COMPUTE_WARP = 4;
 // 16-compute-warp variants (attn_tc_bwd16.cu): 20 warps, four threads per TMEM lane with 16 score columns each. The
 // 8-warp kernels are latency-bound (issue slots 29-37 % busy with 2 compute warps per scheduler, all in the same
 // phase of the load / exp / store sequence: profiles/r01_attn_v8.details.txt); twice the warps with half the columns
-// keep the same instruction count and give every scheduler four warps to interleave. 96 registers per thread at
-// launch (65536 / 640), the producer warpgroup drops to 56, the compute warpgroups take 112.
+// keep the same instruction count and give every scheduler four warps to interleave. Register budget: 96 per thread
+// at launch (65536 / 640 rounded down to the allocation unit of 8), and setmaxnreg only redistributes the CTA's OWN
+// 640 x 96 registers: the producer warpgroup drops to 56 (frees 5120), so the four compute warpgroups can take at
+// most 104 (+4096); asking for 112 blocks forever in setmaxnreg.inc (it hung the first GPU run of this variant).
 constexpr int ATT_COMPUTE_WARPS16 = 16;
 constexpr int ATT_BWD16_THREADS = 128 + 32 * ATT_COMPUTE_WARPS16;
 

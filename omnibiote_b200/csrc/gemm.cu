@@ -373,9 +373,15 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   OBT_REQUIRE(A && B && D, "obt_gemm_bf16: null operand");
   OBT_REQUIRE(M > 0 && N > 0 && K > 0, "obt_gemm_bf16: empty problem M=%lld N=%lld K=%lld", M, N, K);
   OBT_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "obt_gemm_bf16: dims exceed int32");
-  OBT_REQUIRE(((epilogue >= EPI_PLAIN && epilogue <= EPI_RESID_DROPOUT) || (epilogue >= EPI_ROPE && epilogue <= EPI_MUL)) &&
+  OBT_REQUIRE(((epilogue >= EPI_PLAIN && epilogue <= EPI_RESID_DROPOUT) || (epilogue >= EPI_ROPE && epilogue <= EPI_DELTA)) &&
                   epilogue != EPI_PARTIAL,
               "obt_gemm_bf16: bad epilogue %d", epilogue);
+  if (epilogue == EPI_DELTA)
+    // workspace = delta fp32 [M / rope_T, N / 128, rope_T]; the vectorised epilogue path is required (aligned, N % 8)
+    OBT_REQUIRE(aux_in != nullptr && workspace != nullptr && rope_T > 0 && M % rope_T == 0 && N % 128 == 0 &&
+                    workspace_elems >= M * (N / 128) && ld_aux_in % 8 == 0 && ldd % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(aux_in) & 15) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0,
+                "obt_gemm_bf16: epilogue 11 needs aux_in (y), workspace = delta [B, N/128, T] and rope_T = T");
   if (epilogue == EPI_ROPE)
     OBT_REQUIRE(rope_cos != nullptr && rope_T > 0 && rope_head_dim > 0 && rope_head_dim % 8 == 0 && rope_cols % 8 == 0 &&
                     (reinterpret_cast<uintptr_t>(rope_cos) & 15) == 0 && (reinterpret_cast<uintptr_t>(rope_sin) & 15) == 0,
@@ -425,6 +431,8 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   p.rope_cols = rope_cols;
   p.rope_T_mask = (rope_T > 0 && (rope_T & (rope_T - 1)) == 0) ? rope_T - 1 : -1;
   p.rope_d_mask = (rope_head_dim > 0 && (rope_head_dim & (rope_head_dim - 1)) == 0) ? rope_head_dim - 1 : -1;
+  p.delta = epilogue == EPI_DELTA ? static_cast<float*>(workspace) : nullptr;
+  p.delta_T = rope_T;
   auto aligned16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
   p.vec_ok = (N % 8 == 0) && (ldd % 8 == 0) && aligned16(D) &&
              (aux_in == nullptr || epilogue == EPI_ROWMASK || (ld_aux_in % 8 == 0 && aligned16(aux_in))) &&

@@ -29,6 +29,9 @@ enum : int {
                           // DERIVATIVE instead of the pre-activation (one erf evaluation serves both), so that
   EPI_MUL = 10,           // D = rb(rb(acc) * aux_in) is all the backward's epilogue has to do (the GELU' epilogue
                           // was the slowest GEMM of the step: 291 us vs 185 us for the same FLOPs)
+  EPI_DELTA = 11,         // D = rb(acc) and delta[b, h, t] = sum over the 128 columns of head h of D * aux_in: the
+                          // attention backward's per-row dO . O (aux_in = the forward's y), emitted by the GEMM that
+                          // PRODUCES dO = d_a Wo (model.py:151) instead of a separate pass over dO and O
   EPI_ROWMASK = 8,        // D = row_mask[row] ? rb(acc) : 0 with aux_in = uint8 [M]: the MLM head's logits of rows
                           // outside the loss mask are never read (their loss weight and gradient are exactly zero,
                           // train_encoder.py:301-305), so the zeros d loss / d logits needs there are stored right away
@@ -52,6 +55,9 @@ struct GemmParams {
   const float* rope_sin;
   int rope_T, rope_d, rope_cols;
   int rope_T_mask, rope_d_mask;  // T - 1 / d - 1 when they are powers of two (no integer division in the epilogue), else -1
+  // EPI_DELTA: fp32 [B, H, T] with H = N / 128, rows = b * delta_T + t
+  float* delta;
+  int delta_T;
 };
 
 // offset of the 4 table entries of columns gcol..gcol+7 at row grow
@@ -179,7 +185,7 @@ __device__ __forceinline__ void rope8(float (&v)[8], const float4& cs, const flo
 template <int EPI>
 struct EpiTraits {
   static constexpr bool kAuxIn =
-      (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_RESID_DROPOUT || EPI == EPI_MUL);
+      (EPI == EPI_RESID || EPI == EPI_GELU_BWD || EPI == EPI_RESID_DROPOUT || EPI == EPI_MUL || EPI == EPI_DELTA);
   static constexpr bool kAuxOut = (EPI == EPI_GELU || EPI == EPI_GELU_EAGER || EPI == EPI_GELU_DG);
 };
 
@@ -322,6 +328,9 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t taddr, uint8_t* stage, int lane,
                                                 long long row_base, int n0, int split, int c_begin, int c_end) {
   const int rsub = lane >> 3, seg = lane & 7;
+  // EPI_DELTA: per-row partial dot products of this lane's 8 columns, summed over the warp's two 64-column chunks
+  // (= one 128-wide head); rows (hf * 4 + it) * 4 + rsub
+  float dacc0[4] = {0.f, 0.f, 0.f, 0.f}, dacc1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
     const int col_base = n0 + c * 64;
@@ -391,6 +400,12 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
                   for (int e = 0; e < 8; ++e) v[e] = 0.f;
                 }
               }
+              if constexpr (EPI == EPI_DELTA) {
+                float d8 = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d8 = fmaf(v[e], a[e], d8);
+                if (hf == 0) dacc0[it] += d8; else dacc1[it] += d8;
+              }
               epilogue_math<EPI>(p, v, a, u, grow, gcol);
               if constexpr (EpiTraits<EPI>::kAuxOut)
                 *reinterpret_cast<uint4*>(p.aux_out + grow * p.ld_aux_out + gcol) = pack8f(u);
@@ -402,6 +417,25 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
         }
       }
       __syncwarp();  // the staging buffer is reused by the next 64-column chunk
+    }
+  }
+  if constexpr (EPI == EPI_DELTA) {
+    // the 8 lanes of a row group hold the partial sums of 8 columns each: butterfly over seg, lane seg == 0 stores
+    const int head = (n0 + c_begin * 64) >> 7;
+    const int n_heads = p.N >> 7;
+    if (n0 + c_begin * 64 < p.N) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float t = k < 4 ? dacc0[k & 3] : dacc1[k & 3];
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+        const long long grow = row_base + k * 4 + rsub;
+        if (seg == 0 && grow < p.M) {
+          const long long b = grow / p.delta_T, tt = grow - b * p.delta_T;
+          p.delta[(b * n_heads + head) * p.delta_T + tt] = t;
+        }
+      }
     }
   }
 }
@@ -423,6 +457,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const GemmParams& p, uint32_t
     case EPI_ROWMASK: epilogue_chunks<EPI_ROWMASK>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
     case EPI_GELU_DG: epilogue_chunks<EPI_GELU_DG>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
     case EPI_MUL: epilogue_chunks<EPI_MUL>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
+    case EPI_DELTA: epilogue_chunks<EPI_DELTA>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
     default: epilogue_chunks<EPI_GELU_EAGER>(p, taddr, stage, lane, row_base, n0, split, c_begin, c_end); break;
   }
 }

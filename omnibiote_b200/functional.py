@@ -197,9 +197,17 @@ class BlockFunction(torch.autograd.Function):
 
         # ---- attention branch: x1 = x + dropout(y @ Wo^T)
         dw_o = _wgrad(d_a, y, po)
-        dy = ops.gemm(d_a, w_o, b_mn=True)
+        # dy = d_a Wo; with the tensor-core attention (head_dim 128) the same GEMM also emits delta = rowsum(dy * y)
+        # per head from the tile it holds, which the attention backward would otherwise compute in a pass of its own
+        delta = None
+        if d == 128 and ops.ATTN_IMPL in ("auto", "tc") and ops.FUSE_ATTN_DELTA:
+            delta = torch.empty((B, H, T), dtype=torch.float32, device=x.device)
+            dy = ops.gemm(d_a, w_o, b_mn=True, epilogue=ops.EPI_DELTA, aux_in=y, delta=(delta, T))
+        else:
+            dy = ops.gemm(d_a, w_o, b_mn=True)
         # rotary adjoint fused into the dQ / dK epilogues: dqkv is the gradient of c_attn's raw output
-        dqkv = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, ctx.mask, p, ctx.keep, rope=(cos_tab, sin_tab))
+        dqkv = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, ctx.mask, p, ctx.keep, rope=(cos_tab, sin_tab),
+                                 delta=delta)
         dw_qkv = _wgrad(dqkv, h1, pqkv)
         dh1 = ops.gemm(dqkv, w_qkv, b_mn=True)
         acc1 = direct and pg1.grad is not None

@@ -10,7 +10,7 @@ import torch
 from . import _lib
 
 EPI_PLAIN, EPI_RESID, EPI_GELU, EPI_GELU_BWD, EPI_RESID_DROPOUT, EPI_ROPE, EPI_ROWMASK = 0, 1, 2, 3, 5, 7, 8
-EPI_GELU_DG, EPI_MUL = 9, 10
+EPI_GELU_DG, EPI_MUL, EPI_DELTA = 9, 10, 11
 
 # gelu_mode 0: one rounding (TorchScript-fused execution on CUDA); 1: a bf16 rounding per primitive (eager CPU run of
 # the same expression, which is what the CPU oracle does). See SURVEY Appendix A.2.
@@ -21,6 +21,9 @@ GELU_MODE = 0
 import os as _os
 
 ATTN_IMPL = _os.environ.get("OBT_ATTN_IMPL", "auto")
+# delta = rowsum(dO * O) of the attention backward from the epilogue of the GEMM that produces dO (EPI_DELTA) instead of
+# a separate memory-bound pass; OBT_FUSE_ATTN_DELTA=0 restores the stand-alone kernel (A/B runs, tests)
+FUSE_ATTN_DELTA = _os.environ.get("OBT_FUSE_ATTN_DELTA", "1") != "0"
 
 _workspaces: dict = {}
 
@@ -78,9 +81,10 @@ def _mat(t: torch.Tensor, name: str):
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a_mn: bool = False, b_mn: bool = False,
          epilogue: int = EPI_PLAIN, aux_in: torch.Tensor | None = None, aux_out: torch.Tensor | None = None,
          drop_p: float = 0.0, seed: int = 0, offset: int = 0, allow_splitk: bool = True,
-         rope: tuple | None = None) -> torch.Tensor:
+         rope: tuple | None = None, delta: tuple | None = None) -> torch.Tensor:
     """out[M,N] = epilogue(op(a) @ op(b)^T).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn).
-    rope = (cos_tab, sin_tab | None, T, head_dim, n_cols) with epilogue=EPI_ROPE: rotary on the first n_cols columns."""
+    rope = (cos_tab, sin_tab | None, T, head_dim, n_cols) with epilogue=EPI_ROPE: rotary on the first n_cols columns.
+    delta = (delta_out fp32 [B, N/128, T], T) with epilogue=EPI_DELTA: per-head rowsum(out * aux_in)."""
     a, lda = _mat(a, "gemm A")
     b, ldb = _mat(b, "gemm B")
     M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
@@ -101,11 +105,18 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a
     if aux_out is not None:
         aux_out, ld_ao = _mat(aux_out, "gemm aux_out")
     ws, ws_elems = None, 0
-    if allow_splitk and K >= 1024 and M * N <= 8 * 1024 * 1024:
+    rope_T = 0
+    if epilogue == EPI_DELTA:
+        if delta is None or aux_in is None:
+            raise RuntimeError("omnibiote_b200: EPI_DELTA needs aux_in (y) and delta=(fp32 [B, N/128, T], T)")
+        ws, rope_T = delta
+        _req(ws, "delta", torch.float32)
+        ws_elems = ws.numel()
+    elif allow_splitk and K >= 1024 and M * N <= 8 * 1024 * 1024:
         ws_elems = 8 * M * N
         ws = workspace("splitk", ws_elems, torch.float32, a.device)
     rope_cos = rope_sin = None
-    rope_T = rope_d = rope_cols = 0
+    rope_d = rope_cols = 0
     if epilogue == EPI_ROPE:
         if rope is None:
             raise RuntimeError("omnibiote_b200: EPI_ROPE needs rope=(cos, sin, T, head_dim, n_cols)")
@@ -347,10 +358,11 @@ def attention_fwd(qkv: torch.Tensor, B: int, T: int, H: int, d: int, scale: floa
 
 
 def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, keep=None, impl: str = "auto",
-                  rope: tuple | None = None):
+                  rope: tuple | None = None, delta: torch.Tensor | None = None):
     """Returns dqkv [M,3C]: the gradient w.r.t. the post-rotary q,k and v, or, with rope=(cos_tab, sin_tab | None),
     w.r.t. the PRE-rotary c_attn output (the rotary adjoint is applied in the kernels' epilogues).
-    keep: the forward's keep mask."""
+    keep: the forward's keep mask. delta: fp32 [B,H,T] = rowsum(dy * y) per head when the GEMM that produced dy already
+    computed it (ops.gemm(..., epilogue=EPI_DELTA)); tensor-core path only."""
     if drop_p > 0.0 and keep is None:
         raise RuntimeError("omnibiote_b200: attention dropout needs the keep mask (ops.attn_keep_mask)")
     qkv, ld = _mat(qkv, "qkv")
@@ -358,7 +370,11 @@ def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, ke
     C = H * d
     M = B * T
     dqkv = torch.empty((M, 3 * C), dtype=torch.bfloat16, device=qkv.device)
-    delta = torch.empty((B, H, T), dtype=torch.float32, device=qkv.device)
+    delta_ready = delta is not None
+    if delta is None:
+        delta = torch.empty((B, H, T), dtype=torch.float32, device=qkv.device)
+    elif tuple(delta.shape) != (B, H, T) or delta.dtype != torch.float32 or not delta.is_contiguous():
+        raise RuntimeError("omnibiote_b200: precomputed delta must be a contiguous fp32 [B, H, T] tensor")
     esz = 2
     q, k, v = qkv.data_ptr(), qkv.data_ptr() + C * esz, qkv.data_ptr() + 2 * C * esz
     dq, dk, dv = dqkv.data_ptr(), dqkv.data_ptr() + C * esz, dqkv.data_ptr() + 2 * C * esz
@@ -371,7 +387,8 @@ def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, ke
         rc = _lib.load().obt_attn_tc_bwd(qkv.data_ptr(), ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
                                          _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0,
                                          y.data_ptr(), C, dy.data_ptr(), lddy, lse.data_ptr(), delta.data_ptr(),
-                                         dqkv.data_ptr(), 3 * C, B, H, T, d, scale, float(drop_p), _ptr(keep),
+                                         int(delta_ready), dqkv.data_ptr(), 3 * C, B, H, T, d, scale, float(drop_p),
+                                         _ptr(keep),
                                          _ptr(rope[0]) if rope else 0, _ptr(rope[1]) if rope else 0, _stream())
         _lib.check(rc, "obt_attn_tc_bwd")
         return dqkv

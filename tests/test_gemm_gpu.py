@@ -157,6 +157,26 @@ def test_gemm_splitk_wgrad_shape(cg):
         lib.obt_gemm_set_cta_group(0)
 
 
+@pytest.mark.parametrize("cg", [1, 2, 3])
+@pytest.mark.parametrize("B,T,H", [(2, 200, 2), (3, 256, 3), (4, 1024, 8)])
+def test_gemm_delta_epilogue(cg, B, T, H):
+    """Epilogue 11: D = rb(acc) and delta[b, h, t] = sum over head h's 128 columns of D * aux_in (the attention
+    backward's rowsum(dO * O), emitted by the GEMM that produces dO)."""
+    lib, ops = _ops()
+    lib.obt_gemm_set_cta_group(cg)
+    try:
+        M, N, K = B * T, H * 128, 256
+        a, b, ref = _mk(M, N, K, False, True, seed=5)
+        y = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+        delta = torch.full((B, H, T), float("nan"), device="cuda")
+        out = ops.gemm(a, b, b_mn=True, epilogue=ops.EPI_DELTA, aux_in=y, delta=(delta, T))
+        assert torch.equal(out, ops.gemm(a, b, b_mn=True, allow_splitk=False))          # D is the plain result
+        want = (out.float() * y.float()).view(B, T, H, 128).sum(-1).permute(0, 2, 1)    # [B, H, T]
+        assert rel_err(delta, want) < 1e-5 and bool(torch.isfinite(delta).all())
+    finally:
+        lib.obt_gemm_set_cta_group(0)
+
+
 def test_gemm_rejects_bad_arguments():
     lib, ops = _ops()
     a = torch.zeros(16, 12, dtype=torch.bfloat16, device="cuda")  # K=12: pitch not a multiple of 8
