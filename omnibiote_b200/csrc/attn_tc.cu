@@ -66,6 +66,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const int t0 = blockIdx.x * ATT_BM;
   const int h = blockIdx.y, b = blockIdx.z;
   const int T = p.T;
+  // tile metadata precomputed once per micro-batch (obt_attn_tile_meta): one broadcast load issued before anything
+  // else instead of 128 interval loads + shared-memory atomics between the two block barriers below
+  int4 qm = make_int4(T, 0, 0, 0);
+  if (p.qmeta != nullptr)
+    qm = *reinterpret_cast<const int4*>(p.qmeta + (static_cast<long long>(b) * gridDim.x + blockIdx.x) * 4);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_q);
@@ -88,7 +93,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 1) tmem_alloc<1>(tmem_slot, 256);
   __syncthreads();
   // KV tile range covering the union of this tile's visible intervals
-  if (p.row_lo != nullptr && threadIdx.x < ATT_BM && t0 + static_cast<int>(threadIdx.x) < T) {
+  if (p.row_lo != nullptr && p.qmeta == nullptr && threadIdx.x < ATT_BM && t0 + static_cast<int>(threadIdx.x) < T) {
     const int lo = p.row_lo[static_cast<long long>(b) * T + t0 + threadIdx.x];
     const int hi = p.row_hi[static_cast<long long>(b) * T + t0 + threadIdx.x];
     if (lo >= hi) {
@@ -105,9 +110,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   // uniform registers directly instead of a per-lane R2UR waterfall loop around every MMA
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tmem_slot), 0);
   int jb = 0, je = (T + FWD_BN - 1) / FWD_BN;
-  if (p.row_lo != nullptr && s_range[2] == 0 && s_range[1] > s_range[0]) {
-    jb = s_range[0] / FWD_BN;
-    je = (s_range[1] + FWD_BN - 1) / FWD_BN;
+  if (p.row_lo != nullptr) {
+    const int r_lo = p.qmeta ? qm.x : s_range[0], r_hi = p.qmeta ? qm.y : s_range[1];
+    const int r_dead = p.qmeta ? qm.z : s_range[2];
+    if (r_dead == 0 && r_hi > r_lo) {
+      jb = r_lo / FWD_BN;
+      je = (r_hi + FWD_BN - 1) / FWD_BN;
+    }
   }
   const int n_tiles = je - jb;
 
@@ -374,7 +383,7 @@ using namespace obt;
 extern "C" int obt_attn_tc_fwd(const void* qkv, long long ld, const void* mask, long long msb, long long msh,
                                long long msq, const int* row_lo, const int* row_hi, void* y, long long ldy, float* lse,
                                int B, int H, int T, int d, float scale, float drop_p, const unsigned int* keep,
-                               cudaStream_t stream) {
+                               const int* qmeta, cudaStream_t stream) {
   OBT_REQUIRE(qkv && y && lse, "obt_attn_tc_fwd: null pointer");
   OBT_REQUIRE(d == ATT_D, "obt_attn_tc_fwd: head_dim=%d, the tensor-core kernel is specialised for 128", d);
   OBT_REQUIRE(B > 0 && H > 0 && T > 0, "obt_attn_tc_fwd: empty problem");
@@ -400,6 +409,7 @@ extern "C" int obt_attn_tc_fwd(const void* qkv, long long ld, const void* mask, 
   p.msb = msb; p.msh = msh; p.msq = msq;
   p.row_lo = mask ? nullptr : row_lo;
   p.row_hi = mask ? nullptr : row_hi;
+  p.qmeta = (p.row_lo != nullptr) ? qmeta : nullptr;
   p.y = static_cast<__nv_bfloat16*>(y);
   p.ldy = ldy;
   p.lse = lse;

@@ -91,6 +91,11 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
   const int h = blockIdx.y, b = blockIdx.z;
   const int T = p.T;
 
+  // tile metadata precomputed once per micro-batch (obt_attn_tile_meta) instead of a per-CTA scan of the intervals
+  int4 qm = make_int4(T, 0, 0, 0);
+  if (p.qmeta != nullptr)
+    qm = *reinterpret_cast<const int4*>(p.qmeta + (static_cast<long long>(b) * gridDim.x + blockIdx.x) * 4);
+
   // Compute threads (warps 4..11: two per query row, d columns [64*hh, +64)) issue the global loads of their Q and dO
   // half-rows FIRST: ~1 us of latency that now overlaps the barrier / TMEM set-up and the interval scan instead of
   // heading the critical path (17 % of the stall samples of v6, profiles/r01_attn_v8_dq.source.txt).
@@ -128,7 +133,7 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 512);
   __syncthreads();
-  if (p.row_lo != nullptr && threadIdx.x < ATT_BM && t0 + static_cast<int>(threadIdx.x) < T) {
+  if (p.row_lo != nullptr && p.qmeta == nullptr && threadIdx.x < ATT_BM && t0 + static_cast<int>(threadIdx.x) < T) {
     const int lo = p.row_lo[static_cast<long long>(b) * T + t0 + threadIdx.x];
     const int hi = p.row_hi[static_cast<long long>(b) * T + t0 + threadIdx.x];
     if (lo >= hi) {
@@ -149,9 +154,13 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
   auto tile_range = [&](int& jb_out, int& je_out) {
     jb_out = 0;
     je_out = (T + ATT_BN - 1) / ATT_BN;
-    if (p.row_lo != nullptr && s_range[2] == 0 && s_range[1] > s_range[0]) {
-      jb_out = s_range[0] / ATT_BN;
-      je_out = (s_range[1] + ATT_BN - 1) / ATT_BN;
+    if (p.row_lo != nullptr) {
+      const int r_lo = p.qmeta ? qm.x : s_range[0], r_hi = p.qmeta ? qm.y : s_range[1];
+      const int r_dead = p.qmeta ? qm.z : s_range[2];
+      if (r_dead == 0 && r_hi > r_lo) {
+        jb_out = r_lo / ATT_BN;
+        je_out = (r_hi + ATT_BN - 1) / ATT_BN;
+      }
     }
   };
   const int row0 = b * T;
@@ -478,8 +487,12 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     tma_load_2d(&tm_qkv, kv_full, sV, vcol, row0 + j0);
     tma_load_2d(&tm_qkv, kv_full, sV + 16384, vcol + 64, row0 + j0);
   }
-  // which 64-query sub-tiles can see this key tile at all
-  if (p.row_lo != nullptr) {
+  // which 64-query sub-tiles can see this key tile at all: precomputed once per micro-batch (obt_attn_tile_meta) or,
+  // without it, scanned here
+  if (p.row_lo != nullptr && p.kmeta != nullptr) {
+    if (threadIdx.x < 4)
+      s_rel[threadIdx.x] = p.kmeta[(static_cast<long long>(b) * gridDim.x + blockIdx.x) * 4 + threadIdx.x];
+  } else if (p.row_lo != nullptr) {
     // four rows per thread and pass: all loads in flight before the first dependent atomic
     for (int i0 = threadIdx.x; i0 < T; i0 += 4 * blockDim.x) {
       int lo[4], hi[4];
@@ -848,18 +861,18 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
 using namespace obt;
 
-// attn_tc_bwd16.cu
-int launch_attn_tc_dq16(const CUtensorMap& tm_qkv, const void* qkv, long long ld, const void* dy, long long lddy,
-                        const AttnTcParams& p, int C, dim3 grid, bool drop, cudaStream_t stream);
-int launch_attn_tc_dkv16(const CUtensorMap& tm_qkv, const CUtensorMap& tm_q64, const CUtensorMap& tm_dy64,
-                         const AttnTcParams& p, int C, dim3 grid, bool drop, cudaStream_t stream);
+// attn_tc_bwd_persist.cu
+int launch_attn_tc_dq_persist(const CUtensorMap& tm_qkv, const void* qkv, long long ld, const void* dy, long long lddy,
+                              const AttnTcParams& p, int C, int* sched, bool drop, cudaStream_t stream);
+int launch_attn_tc_dkv_persist(const CUtensorMap& tm_qkv, const CUtensorMap& tm_q64, const CUtensorMap& tm_dy64,
+                               const AttnTcParams& p, int C, int* sched, bool drop, cudaStream_t stream);
 
-// OBT_ATTN_BWD_WARPS=8|16 overrides the number of compute warps of the backward kernels (A/B runs)
-static int attn_bwd_compute_warps() {
-  const char* e = getenv("OBT_ATTN_BWD_WARPS");
-  if (e != nullptr && e[0] == '8') return 8;
-  if (e != nullptr && e[0] == '1' && e[1] == '6') return 16;
-  return 8;
+// OBT_ATTN_PERSIST: bit 0 = persistent dQ kernel, bit 1 = persistent dK/dV kernel (default 3 = both when the caller
+// passes scheduler counters; 0 = the one-CTA-per-item kernels; A/B runs)
+static int attn_persist_mask() {
+  const char* e = getenv("OBT_ATTN_PERSIST");
+  if (e != nullptr && e[0] >= '0' && e[0] <= '3') return e[0] - '0';
+  return 3;
 }
 
 extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, long long msb, long long msh,
@@ -867,7 +880,7 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
                                const void* dy, long long lddy, const float* lse, float* delta, int delta_ready,
                                void* dqkv, long long ldd, int B, int H, int T, int d, float scale, float drop_p,
                                const unsigned int* keep, const float* rope_cos, const float* rope_sin,
-                               cudaStream_t stream) {
+                               const int* qmeta, const unsigned int* kmeta, int* sched, cudaStream_t stream) {
   OBT_REQUIRE(qkv && y && dy && lse && delta && dqkv, "obt_attn_tc_bwd: null pointer");
   OBT_REQUIRE((reinterpret_cast<uintptr_t>(rope_cos) & 15) == 0 && (reinterpret_cast<uintptr_t>(rope_sin) & 15) == 0,
               "obt_attn_tc_bwd: rotary tables must be 16-byte aligned");
@@ -905,6 +918,8 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
   p.msb = msb; p.msh = msh; p.msq = msq;
   p.row_lo = mask ? nullptr : row_lo;
   p.row_hi = mask ? nullptr : row_hi;
+  p.qmeta = (p.row_lo != nullptr) ? qmeta : nullptr;
+  p.kmeta = (p.row_lo != nullptr) ? kmeta : nullptr;
   p.lse = const_cast<float*>(lse);
   p.delta = delta;
   p.drop_p = drop_p;
@@ -929,22 +944,20 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
     attr_set = true;
   }
   dim3 grid((T + ATT_BM - 1) / ATT_BM, H, B);
-  if (attn_bwd_compute_warps() == 16) {
-    rc = launch_attn_tc_dq16(tm_qkv, qkv, ld, dy, lddy, p, C, grid, drop_p > 0.f, stream);
-  } else {
-    if (drop_p > 0.f)
-      attn_tc_dq_kernel<true><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(
-          tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
-    else
-      attn_tc_dq_kernel<false><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(
-          tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
-    rc = check_launch("attn_tc_dq");
-  }
+  // persistent kernels: need the scheduler counters; with an interval mask the dK/dV one also needs the relevance bits
+  const int persist = (sched != nullptr) ? attn_persist_mask() : 0;
+  const bool dkv_persist = (persist & 2) && (p.row_lo == nullptr || p.kmeta != nullptr);
+  if (persist & 1) {
+    rc = launch_attn_tc_dq_persist(tm_qkv, qkv, ld, dy, lddy, p, C, sched, drop_p > 0.f, stream);
+  } else if (drop_p > 0.f)
+    attn_tc_dq_kernel<true><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(
+        tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
+  else
+    attn_tc_dq_kernel<false><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(
+        tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
+  if (!(persist & 1)) rc = check_launch("attn_tc_dq");
   if (rc) return rc;
-  // OBT_ATTN_DKV_WARPS overrides the dK/dV kernel alone (A/B runs)
-  int dkv_warps = attn_bwd_compute_warps();
-  if (const char* e = getenv("OBT_ATTN_DKV_WARPS")) dkv_warps = (e[0] == '1' && e[1] == '6') ? 16 : 8;
-  if (dkv_warps == 16) return launch_attn_tc_dkv16(tm_qkv, tm_q64, tm_dy64, p, C, grid, drop_p > 0.f, stream);
+  if (dkv_persist) return launch_attn_tc_dkv_persist(tm_qkv, tm_q64, tm_dy64, p, C, sched, drop_p > 0.f, stream);
   if (drop_p > 0.f)
     attn_tc_dkv_kernel<true><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
   else

@@ -20,6 +20,9 @@ struct AttnTcParams {
   long long msb, msh, msq;
   const int* row_lo;
   const int* row_hi;
+  // optional tile metadata of the interval mask (obt_attn_tile_meta): saves every CTA its own scan of the intervals
+  const int* qmeta;            // [B, ceil(T/128), 4] = {min lo, max hi, any fully-masked row, 0} per 128-query tile
+  const unsigned int* kmeta;   // [B, ceil(T/128), 4] = relevance bits of the 64-query sub-tiles per 128-key tile
   // forward outputs / backward inputs
   __nv_bfloat16* y;
   long long ldy;
@@ -118,42 +121,6 @@ __device__ __forceinline__ void issue_grad_ts_128x128x64(uint32_t d_tmem, uint32
   }
 }
 
-// Same with A written as FOUR 8-column pieces, one per K-step of 16 reduction indices, 16 columns apart (the
-// 16-compute-warp kernels: four threads per TMEM lane, each owning 16 score columns and writing its 8 packed words
-// over the first 8 of them).
-__device__ __forceinline__ void issue_grad_ts_128x128x64_q16(uint32_t d_tmem, uint32_t a_base, uint32_t b_addr,
-                                                             uint32_t b_lbo, bool accumulate) {
-  constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, true);
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    const uint64_t b_desc = make_smem_desc_sw128(b_addr + kk * 2048, b_lbo, 1024);
-    umma_bf16_ts(d_tmem, a_base + kk * 16, b_desc, idesc, (accumulate || kk > 0) ? 1u : 0u);
-  }
-}
-
-// adjoint rotary on 16 consecutive d-columns (8 pairs): cs / sn = the 8 table entries (2 x float4)
-__device__ __forceinline__ void rope_adjoint16(float (&f)[16], const float4* cs, const float4* sn, bool has_sin) {
-#pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    const float c[4] = {cs[g].x, cs[g].y, cs[g].z, cs[g].w};
-    if (has_sin) {
-      const float s4[4] = {sn[g].x, sn[g].y, sn[g].z, sn[g].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float a = f[g * 8 + 2 * j], b = f[g * 8 + 2 * j + 1];
-        f[g * 8 + 2 * j] = a * c[j] + b * s4[j];
-        f[g * 8 + 2 * j + 1] = b * c[j] - a * s4[j];
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        f[g * 8 + 2 * j] *= c[j];
-        f[g * 8 + 2 * j + 1] *= c[j];
-      }
-    }
-  }
-}
-
 // bit k set <=> position base + k lies in [lo, hi), k = 0..31
 __device__ __forceinline__ uint32_t interval_bits32(int lo, int hi, int base) {
   const int a = min(max(lo - base, 0), 32), b = min(max(hi - base, 0), 32);
@@ -169,14 +136,10 @@ constexpr int ATT_COMPUTE_WARPS = 8;
 // spilled in the compute loops and reloaded the spills on the critical path (profiles/r01_attn_v7_bwd.source.txt).
 constexpr int ATT_BWD_THREADS = 384;
 constexpr int ATT_BWD_FIRST_COMPUTE_WARP = 4;
-// 16-compute-warp variants (attn_tc_bwd16.cu): 20 warps, four threads per TMEM lane with 16 score columns each. The
-// 8-warp kernels are latency-bound (issue slots 29-37 % busy with 2 compute warps per scheduler, all in the same
-// phase of the load / exp / store sequence: profiles/r01_attn_v8.details.txt); twice the warps with half the columns
-// keep the same instruction count and give every scheduler four warps to interleave. Register budget: 96 per thread
-// at launch (65536 / 640 rounded down to the allocation unit of 8), and setmaxnreg only redistributes the CTA's OWN
-// 640 x 96 registers: the producer warpgroup drops to 56 (frees 5120), so the four compute warpgroups can take at
-// most 104 (+4096); asking for 112 blocks forever in setmaxnreg.inc (it hung the first GPU run of this variant).
-constexpr int ATT_COMPUTE_WARPS16 = 16;
-constexpr int ATT_BWD16_THREADS = 128 + 32 * ATT_COMPUTE_WARPS16;
+// Measured and rejected (round 2, profiles/r02c_attn_bwd_w16.details.txt): 16 compute warps with 16 score columns each
+// (four threads per TMEM lane; 96 registers at launch, setmaxnreg to 104 because it only redistributes the CTA's own
+// 640 x 96 registers) raised the IPC (1.13 -> 1.38, 1.45 -> 1.94) but not the speed: dQ 211.8 -> 220.8 us, dK/dV
+// 267.6 -> 308.5 us. The sub-tile loop is bound by the dependency chain dS(s) -> [dQ += dS K ; S(s+2), dP(s+2)] ->
+// compute(s+2) through the two TMEM score buffers, and ~45 % of a CTA's life is fixed prologue / epilogue latency.
 
 }  // namespace obt

@@ -240,6 +240,61 @@ extern "C" int obt_mlm_mask(const long long* ids, long long* masked_ids, unsigne
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tile metadata of an interval mask, computed ONCE per micro-batch and shared by every layer, head and attention
+// kernel (forward, dQ, dK/dV): each of their CTAs used to re-derive it from the per-row intervals in its prologue
+// (loads + shared-memory atomics + a block barrier in front of the first TMA / MMA; ~45 % of a backward CTA's life is
+// such fixed latency, profiles/r02c_attn_dq_w8.source.txt).
+//   qmeta[b][tq] = {min lo, max hi, any fully-masked row, 0} over the 128 query rows of tile tq
+//   kmeta[b][tk] = 128 relevance bits: bit it set <=> the 64-query sub-tile `it` has a row that sees a key of the
+//                  128-key tile tk, or a fully-masked row (those attend to every key)
+// ---------------------------------------------------------------------------------------------
+namespace obt {
+__global__ void attn_tile_meta_kernel(const int* __restrict__ row_lo, const int* __restrict__ row_hi, int T,
+                                      int* __restrict__ qmeta, unsigned int* __restrict__ kmeta) {
+  __shared__ int s_q[3];
+  __shared__ unsigned int s_rel[4];
+  const int tile = blockIdx.x, b = blockIdx.y, nT = gridDim.x;
+  if (threadIdx.x == 0) {
+    s_q[0] = T; s_q[1] = 0; s_q[2] = 0;
+    s_rel[0] = s_rel[1] = s_rel[2] = s_rel[3] = 0u;
+  }
+  __syncthreads();
+  const int* lo = row_lo + static_cast<long long>(b) * T;
+  const int* hi = row_hi + static_cast<long long>(b) * T;
+  const int i = tile * 128 + threadIdx.x;
+  if (threadIdx.x < 128 && i < T) {
+    const int l = lo[i], h = hi[i];
+    if (l >= h) {
+      atomicExch(&s_q[2], 1);
+    } else {
+      atomicMin(&s_q[0], l);
+      atomicMax(&s_q[1], h);
+    }
+  }
+  const int j0 = tile * 128;
+  for (int r = threadIdx.x; r < T; r += blockDim.x) {
+    const int l = lo[r], h = hi[r];
+    if ((l >= h) || (l < j0 + 128 && h > j0)) atomicOr(&s_rel[(r >> 6) >> 5], 1u << ((r >> 6) & 31));
+  }
+  __syncthreads();
+  const long long o = (static_cast<long long>(b) * nT + tile) * 4;
+  if (threadIdx.x < 4) {
+    qmeta[o + threadIdx.x] = threadIdx.x < 3 ? s_q[threadIdx.x] : 0;
+    kmeta[o + threadIdx.x] = s_rel[threadIdx.x];
+  }
+}
+}  // namespace obt
+
+extern "C" int obt_attn_tile_meta(const int* row_lo, const int* row_hi, int B, int T, int* qmeta, unsigned int* kmeta,
+                                  cudaStream_t stream) {
+  OBT_REQUIRE(row_lo && row_hi && qmeta && kmeta, "obt_attn_tile_meta: null pointer");
+  OBT_REQUIRE(B > 0 && T > 0 && T <= 128 * 64, "obt_attn_tile_meta: bad B=%d T=%d", B, T);
+  dim3 grid((T + 127) / 128, B);
+  obt::attn_tile_meta_kernel<<<grid, 256, 0, stream>>>(row_lo, row_hi, T, qmeta, kmeta);
+  return check_launch("attn_tile_meta");
+}
+
+// ---------------------------------------------------------------------------------------------
 // Row compaction for the masked-rows-only head (d loss / d logits is exactly zero on the ~85 % of
 // rows outside the MLM mask, so the head GEMMs, the CE and their backward only need the masked rows).
 //   compact_rows : stable list of the rows with mask != 0 -> idx[0..count), padded with -1 up to `cap`; the targets of

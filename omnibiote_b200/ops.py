@@ -277,10 +277,27 @@ def pool_bwd(emb, pooled, dout, mode: str) -> torch.Tensor:
 class MaskSpec:
     """Additive attention mask as the kernels consume it: a bf16 tensor plus (batch, head, query) strides."""
 
-    __slots__ = ("tensor", "msb", "msh", "msq", "row_lo", "row_hi")
+    __slots__ = ("tensor", "msb", "msh", "msq", "row_lo", "row_hi", "_meta")
+
+    def tile_meta(self):
+        """(qmeta, kmeta) of the interval form (obt_attn_tile_meta), computed on first use and shared by every layer
+        and attention kernel of the micro-batch; (None, None) for dense / absent masks."""
+        if self.tensor is not None or self.row_lo is None:
+            return None, None
+        if self._meta is None:
+            B, T = self.row_lo.shape
+            nT = (T + 127) // 128
+            qmeta = torch.empty((B, nT, 4), dtype=torch.int32, device=self.row_lo.device)
+            kmeta = torch.empty((B, nT, 4), dtype=torch.int32, device=self.row_lo.device)
+            rc = _lib.load().obt_attn_tile_meta(self.row_lo.data_ptr(), self.row_hi.data_ptr(), B, T, qmeta.data_ptr(),
+                                                kmeta.data_ptr(), _stream())
+            _lib.check(rc, "obt_attn_tile_meta")
+            self._meta = (qmeta, kmeta)
+        return self._meta
 
     def __init__(self, attn_mask: torch.Tensor | None, B: int, H: int, T: int, row_lo=None, row_hi=None):
         self.tensor = None
+        self._meta = None
         self.msb = self.msh = self.msq = 0
         # optional interval form (int32 [B,T] each): key j visible to query (b,i) iff lo <= j < hi
         self.row_lo, self.row_hi = row_lo, row_hi
@@ -345,9 +362,10 @@ def attention_fwd(qkv: torch.Tensor, B: int, T: int, H: int, d: int, scale: floa
                                            and mask.tensor.data_ptr() % 16 == 0)
         impl = "tc" if (d == 128 and dense_ok) else "simt"
     if impl == "tc":
+        qmeta = mask.tile_meta()[0] if use_iv else None
         rc = lib.obt_attn_tc_fwd(qkv.data_ptr(), ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
                                  _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0, y.data_ptr(), C,
-                                 lse.data_ptr(), B, H, T, d, scale, float(drop_p), _ptr(keep), _stream())
+                                 lse.data_ptr(), B, H, T, d, scale, float(drop_p), _ptr(keep), _ptr(qmeta), _stream())
         _lib.check(rc, "obt_attn_tc_fwd")
         return y, lse
     rc = lib.obt_attn_simt_fwd(q, k, v, ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
@@ -384,12 +402,16 @@ def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, ke
     if impl == "auto":
         impl = "tc" if d == 128 else "simt"
     if impl == "tc":
+        qmeta, kmeta = mask.tile_meta() if use_iv else (None, None)
+        # work counters of the persistent backward kernels: zero on first use, left zero by the kernels
+        sched = workspace("attn_sched", 32, torch.int32, qkv.device, zero=True)
         rc = _lib.load().obt_attn_tc_bwd(qkv.data_ptr(), ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
                                          _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0,
                                          y.data_ptr(), C, dy.data_ptr(), lddy, lse.data_ptr(), delta.data_ptr(),
                                          int(delta_ready), dqkv.data_ptr(), 3 * C, B, H, T, d, scale, float(drop_p),
                                          _ptr(keep),
-                                         _ptr(rope[0]) if rope else 0, _ptr(rope[1]) if rope else 0, _stream())
+                                         _ptr(rope[0]) if rope else 0, _ptr(rope[1]) if rope else 0, _ptr(qmeta),
+                                         _ptr(kmeta), sched.data_ptr(), _stream())
         _lib.check(rc, "obt_attn_tc_bwd")
         return dqkv
     rc = _lib.load().obt_attn_simt_bwd(q, k, v, ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,

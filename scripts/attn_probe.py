@@ -21,7 +21,7 @@ from omnibiote_b200 import ops  # noqa: E402
 def main():
     B, H, T, d = int(os.environ.get("PROBE_B", 32)), 8, int(os.environ.get("PROBE_T", 1024)), 128
     p = float(os.environ.get("PROBE_P", 0.1))
-    reps = int(os.environ.get("PROBE_REPS", 20))
+    reps = int(os.environ.get("PROBE_REPS", 50))
     C, dev = H * d, torch.device("cuda", 0)
     scale = 8.0 / C
     g = torch.Generator(device=dev).manual_seed(0)
@@ -33,7 +33,7 @@ def main():
     keep = ops.attn_keep_mask(B, H, T, p, 1, 0, dev) if p > 0 else None
 
     def timed(fn):
-        for _ in range(3):
+        for _ in range(min(10, max(3, reps // 4))):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -68,7 +68,11 @@ def main():
     out = {"B": B, "T": T, "drop_p": p, "fwd_ms": ms_f, "bwd_ms": ms_b, "keep_mask_ms": ms_k,
            "fwd_model_tflops": flops_f / ms_f / 1e9, "bwd_model_tflops": 2.5 * flops_f / ms_b / 1e9,
            "fwd_rel_err": rel(y[b0], ref.detach()), "bwd_rel_err": rel(dqkv[b0], ref_g),
-           "variant": os.environ.get("OBT_ATTN_VARIANT", "default")}
+           "variant": os.environ.get("OBT_ATTN_VARIANT", "default"), "persist": os.environ.get("OBT_ATTN_PERSIST", "3")}
+    if os.environ.get("OBT_ATTN_PERSIST", "3") != "0":  # whole-tensor equality with the one-CTA-per-item kernels
+        os.environ["OBT_ATTN_PERSIST"] = "0"
+        ref = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, spec, p, keep, impl="tc")
+        out["equals_per_item_kernels"] = bool(torch.equal(ref, dqkv))
     print(json.dumps(out))
 
 

@@ -9,13 +9,11 @@ pytestmark = pytest.mark.gpu
 BF = torch.bfloat16
 
 
-@pytest.fixture(autouse=True, params=[8, 16], ids=["bwd8warps", "bwd16warps"])
+@pytest.fixture(autouse=True, params=["0", "3"], ids=["bwd_per_item", "bwd_persistent"])
 def _backward_variant(request, monkeypatch):
-    """every test of this module runs with both layouts of the backward kernels (8 / 16 compute warps)"""
-    import os
-    if request.param == 16 and os.environ.get("OBT_SKIP_W16"):
-        pytest.skip("16-warp backward disabled for this run (OBT_SKIP_W16)")
-    monkeypatch.setenv("OBT_ATTN_BWD_WARPS", str(request.param))
+    """every test of this module runs with both forms of the backward kernels: one CTA per work item (legacy) and
+    persistent CTAs fetching items from a device counter (OBT_ATTN_PERSIST, csrc/attn_tc_bwd_persist.cu)"""
+    monkeypatch.setenv("OBT_ATTN_PERSIST", request.param)
     yield
 
 
@@ -201,3 +199,64 @@ def test_attn_dropout_same_mask_in_both_kernels_and_in_backward():
     g_tc = ops.attention_bwd(qkv, y_tc, dy, lse_tc, B, T, H, d, scale, spec, p, keep, impl="tc")
     g_si = ops.attention_bwd(qkv, y_si, dy, lse_si, B, T, H, d, scale, spec, p, keep, impl="simt")
     assert rel_err(g_tc, g_si) < 2e-2
+
+
+def test_tile_metadata_of_interval_masks():
+    """obt_attn_tile_meta against a torch restatement: per 128-query tile {min lo, max hi, any fully-masked row}, per
+    128-key tile the relevance bits of the 64-query sub-tiles."""
+    from omnibiote_b200 import ops
+    B, T = 3, 700
+    ids = _doc_ids(B, T, 5)
+    ids[1, 600:] = 1  # padded tail -> fully-masked rows with padding=True
+    lo, hi = ops.doc_mask_intervals(ids, 3, True)
+    spec = ops.MaskSpec(None, B, 2, T, lo, hi)
+    qmeta, kmeta = spec.tile_meta()
+    assert spec.tile_meta()[0] is qmeta                                 # cached: one launch per micro-batch
+    nT = (T + 127) // 128
+    lo_c, hi_c = lo.cpu(), hi.cpu()
+    for b in range(B):
+        for t in range(nT):
+            rows = slice(t * 128, min(T, (t + 1) * 128))
+            l, h = lo_c[b, rows], hi_c[b, rows]
+            dead = l >= h
+            live = ~dead
+            want = [int(l[live].min()) if live.any() else T, int(h[live].max()) if live.any() else 0, int(dead.any()), 0]
+            assert qmeta[b, t].tolist() == want, (b, t)
+            bits = 0
+            for it in range((T + 63) // 64):
+                r = slice(it * 64, min(T, (it + 1) * 64))
+                ll, hh = lo_c[b, r], hi_c[b, r]
+                if bool(((ll >= hh) | ((ll < t * 128 + 128) & (hh > t * 128))).any()):
+                    bits |= 1 << it
+            got = sum((int(kmeta[b, t, w]) & 0xffffffff) << (32 * w) for w in range(4))
+            assert got == bits, (b, t, hex(got), hex(bits))
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_persistent_backward_many_items_per_cta_equals_per_item_kernels(p_drop, monkeypatch):
+    """More work items (B * H * T/128 = 512) than SMs: every persistent CTA runs several items back to back (barrier
+    phases, TMEM accumulators and the K/V / Q/dO rings carried across items). Same arithmetic in the same order per
+    item, so the result must equal the one-CTA-per-item kernels bit for bit."""
+    from omnibiote_b200 import ops
+    B, T, H, d = 8, 1024, 8, 128
+    C = H * d
+    g = torch.Generator(device="cuda").manual_seed(3)
+    qkv = torch.randn(B * T, 3 * C, generator=g, device="cuda").to(BF)
+    dy = (torch.randn(B * T, C, generator=g, device="cuda") * 0.1).to(BF)
+    ids = _doc_ids(B, T, 9)
+    ids[2, 900:] = 1
+    lo, hi = ops.doc_mask_intervals(ids, 3, True)
+    keep = ops.attn_keep_mask(B, H, T, p_drop, 7, 0, qkv.device) if p_drop > 0 else None
+    out = {}
+    for mode, spec in (("interval", ops.MaskSpec(None, B, H, T, lo, hi)), ("none", ops.MaskSpec(None, B, H, T))):
+        y, lse = ops.attention_fwd(qkv, B, T, H, d, 8.0 / C, spec, p_drop, keep, impl="tc")
+        for persist in ("0", "1", "2", "3"):
+            monkeypatch.setenv("OBT_ATTN_PERSIST", persist)
+            for rep in range(2):  # twice: the work counters must be back at zero after a launch
+                out[(mode, persist, rep)] = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, 8.0 / C, spec, p_drop, keep,
+                                                              impl="tc")
+        for persist in ("1", "2", "3"):
+            for rep in range(2):
+                assert torch.equal(out[(mode, persist, rep)], out[(mode, "0", 0)]), (mode, persist, rep)
+    sched = ops._workspaces[("attn_sched", torch.int32, qkv.device)]
+    assert int(sched.abs().sum()) == 0

@@ -83,13 +83,8 @@ def test_rope_real_table_is_cosine_scaling_and_complex_is_rotation():
     assert rel_err(back[:, :2 * C], qkv[:, :2 * C]) < 8e-3
 
 
-@pytest.mark.parametrize("bwd_warps", [8, 16])
 @pytest.mark.parametrize("complex_table", [False, True])
-def test_rope_fused_into_gemm_epilogue_and_attention_backward(complex_table, bwd_warps, monkeypatch):
-    import os
-    if bwd_warps == 16 and os.environ.get("OBT_SKIP_W16"):
-        pytest.skip("16-warp backward disabled for this run (OBT_SKIP_W16)")
-    monkeypatch.setenv("OBT_ATTN_BWD_WARPS", str(bwd_warps))
+def test_rope_fused_into_gemm_epilogue_and_attention_backward(complex_table):
     """The fused paths (c_attn GEMM epilogue; dQ / dK epilogues of the attention backward) against the stand-alone
     rotary kernel applied to the un-fused results."""
     ops = _ops()
