@@ -861,26 +861,20 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
 using namespace obt;
 
-// attn_tc_bwd_persist.cu
-int launch_attn_tc_dq_persist(const CUtensorMap& tm_qkv, const void* qkv, long long ld, const void* dy, long long lddy,
-                              const AttnTcParams& p, int C, int* sched, bool drop, cudaStream_t stream);
-int launch_attn_tc_dkv_persist(const CUtensorMap& tm_qkv, const CUtensorMap& tm_q64, const CUtensorMap& tm_dy64,
-                               const AttnTcParams& p, int C, int* sched, bool drop, cudaStream_t stream);
-
-// OBT_ATTN_PERSIST: bit 0 = persistent dQ kernel, bit 1 = persistent dK/dV kernel (default 3 = both when the caller
-// passes scheduler counters; 0 = the one-CTA-per-item kernels; A/B runs)
-static int attn_persist_mask() {
-  const char* e = getenv("OBT_ATTN_PERSIST");
-  if (e != nullptr && e[0] >= '0' && e[0] <= '3') return e[0] - '0';
-  return 3;
-}
+// Measured and rejected (round 2): persistent forms of both kernels (one CTA per SM fetching (tile, head, batch) items
+// from a device counter, the TMA producer running ahead across items, Q / dO of the next item loaded before the
+// accumulator read-out). Bit-identical results, but dQ 211.4 -> 198.4 us and dK/dV 257.9 -> 322.9 us stand-alone and
+// no gain inside the step (profiles/r02d_attn_probe_launches_*.txt, r02d_attn_bwd_persist.details.txt): the per-item
+// latencies that remain (first parameter loads, first score product, accumulator read-out) are on the compute warps'
+// critical path in either form, and the sub-tile loop itself (MUFU 512 cycles + ~600 cycles of FP32 / pack / TMEM
+// traffic per 64 keys on 8 warps, against 768 cycles of MMA) sets the pace.
 
 extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, long long msb, long long msh,
                                long long msq, const int* row_lo, const int* row_hi, const void* y, long long ldy,
                                const void* dy, long long lddy, const float* lse, float* delta, int delta_ready,
                                void* dqkv, long long ldd, int B, int H, int T, int d, float scale, float drop_p,
                                const unsigned int* keep, const float* rope_cos, const float* rope_sin,
-                               const int* qmeta, const unsigned int* kmeta, int* sched, cudaStream_t stream) {
+                               const int* qmeta, const unsigned int* kmeta, cudaStream_t stream) {
   OBT_REQUIRE(qkv && y && dy && lse && delta && dqkv, "obt_attn_tc_bwd: null pointer");
   OBT_REQUIRE((reinterpret_cast<uintptr_t>(rope_cos) & 15) == 0 && (reinterpret_cast<uintptr_t>(rope_sin) & 15) == 0,
               "obt_attn_tc_bwd: rotary tables must be 16-byte aligned");
@@ -944,20 +938,14 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
     attr_set = true;
   }
   dim3 grid((T + ATT_BM - 1) / ATT_BM, H, B);
-  // persistent kernels: need the scheduler counters; with an interval mask the dK/dV one also needs the relevance bits
-  const int persist = (sched != nullptr) ? attn_persist_mask() : 0;
-  const bool dkv_persist = (persist & 2) && (p.row_lo == nullptr || p.kmeta != nullptr);
-  if (persist & 1) {
-    rc = launch_attn_tc_dq_persist(tm_qkv, qkv, ld, dy, lddy, p, C, sched, drop_p > 0.f, stream);
-  } else if (drop_p > 0.f)
+  if (drop_p > 0.f)
     attn_tc_dq_kernel<true><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(
         tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
   else
     attn_tc_dq_kernel<false><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(
         tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
-  if (!(persist & 1)) rc = check_launch("attn_tc_dq");
+  rc = check_launch("attn_tc_dq");
   if (rc) return rc;
-  if (dkv_persist) return launch_attn_tc_dkv_persist(tm_qkv, tm_q64, tm_dy64, p, C, sched, drop_p > 0.f, stream);
   if (drop_p > 0.f)
     attn_tc_dkv_kernel<true><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
   else

@@ -26,13 +26,18 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // keep/scale decision for element `e` of a flat tensor; 4 consecutive elements share one Philox call.
+// keep <=> (r >> 8) * 2^-24 >= p  <=>  (r >> 8) >= ceil(p * 2^24): both sides of the float comparison are exact (a 24-bit
+// integer scaled by a power of two, p scaled by a power of two), so the integer form selects the same elements as the
+// GEMM epilogue's float form with one compare instead of convert + multiply + compare per element.
+__device__ __forceinline__ uint32_t dropout_threshold(float p) { return static_cast<uint32_t>(ceilf(p * 16777216.0f)); }
 __device__ __forceinline__ void dropout4(unsigned long long seed, unsigned long long offset, unsigned long long e4,
                                          float p, bool (&keep)[4]) {
+  const uint32_t thr = dropout_threshold(p);  // loop-invariant: hoisted by the compiler
   uint4 r = rand4x32(seed, e4, offset);
-  keep[0] = (r.x >> 8) * (1.0f / 16777216.0f) >= p;
-  keep[1] = (r.y >> 8) * (1.0f / 16777216.0f) >= p;
-  keep[2] = (r.z >> 8) * (1.0f / 16777216.0f) >= p;
-  keep[3] = (r.w >> 8) * (1.0f / 16777216.0f) >= p;
+  keep[0] = (r.x >> 8) >= thr;
+  keep[1] = (r.y >> 8) >= thr;
+  keep[2] = (r.z >> 8) >= thr;
+  keep[3] = (r.w >> 8) >= thr;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -221,9 +226,11 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
               __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop, float* __restrict__ dgamma_partial,
               unsigned int* __restrict__ sync_counter, __nv_bfloat16* __restrict__ dgamma, int accumulate_dgamma,
               long long M, int C, float dy_div, float drop_p, unsigned long long seed, unsigned long long offset) {
-  // dgamma partial sums live in shared memory, laid out [warp][chunk i][j][lane] (lane fastest: conflict-free), so
-  // the row loop needs ~70 registers and three 256-thread blocks fit per SM (the register-resident version ran one
-  // block per SM and reached 1.6 TB/s; see profiles/r01_launches_v3.txt).
+  // dgamma partial sums: 32 fp32 accumulators per lane in registers (fixed lane -> column mapping), written once per
+  // block to shared memory [warp][chunk i][j][lane] (lane fastest: conflict-free) for the block reduction. The kernel
+  // is instruction-issue bound since the dropout replay moved in (60 % issue slots busy, 3.5 TB/s,
+  // profiles/r02c_ln_bwd.details.txt): the shared-memory read-modify-write per element cost 3 instructions, the
+  // accumulators fit in the 128 registers two resident blocks per SM allow.
   extern __shared__ float s_dg[];
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5;
@@ -231,10 +238,11 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
   const int nchunks = C / 8;
   const float drop_scale = 1.0f / (1.0f - drop_p);
   float* my_dg = s_dg + static_cast<size_t>(warp) * kMaxChunks * 256;
+  float dg_acc[kMaxChunks][8];
 #pragma unroll
   for (int i = 0; i < kMaxChunks; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) my_dg[(i * 8 + j) * 32 + lane] = 0.f;
+    for (int j = 0; j < 8; ++j) dg_acc[i][j] = 0.f;
 
   for (long long row = static_cast<long long>(blockIdx.x) * warps_per_block + warp; row < M;
        row += static_cast<long long>(gridDim.x) * warps_per_block) {
@@ -273,7 +281,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
         for (int j = 0; j < 8; ++j) {
           const float xh = (xv[j] - mean) * rstd;
           const float a = d[j] * g[j];
-          my_dg[(i * 8 + j) * 32 + lane] += d[j] * xh;
+          dg_acc[i][j] = fmaf(d[j], xh, dg_acc[i][j]);
           s1 += a;
           s2 += a * xh;
         }
@@ -317,6 +325,10 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
       }
     }
   }
+#pragma unroll
+  for (int i = 0; i < kMaxChunks; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) my_dg[(i * 8 + j) * 32 + lane] = dg_acc[i][j];
   __syncthreads();
   // block reduction of the per-warp dgamma partials; column of (i, j, lane) = (lane + 32 i) * 8 + j
   for (int t = threadIdx.x; t < kMaxChunks * 256; t += blockDim.x) {

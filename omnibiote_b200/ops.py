@@ -403,15 +403,13 @@ def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, ke
         impl = "tc" if d == 128 else "simt"
     if impl == "tc":
         qmeta, kmeta = mask.tile_meta() if use_iv else (None, None)
-        # work counters of the persistent backward kernels: zero on first use, left zero by the kernels
-        sched = workspace("attn_sched", 32, torch.int32, qkv.device, zero=True)
         rc = _lib.load().obt_attn_tc_bwd(qkv.data_ptr(), ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
                                          _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0,
                                          y.data_ptr(), C, dy.data_ptr(), lddy, lse.data_ptr(), delta.data_ptr(),
                                          int(delta_ready), dqkv.data_ptr(), 3 * C, B, H, T, d, scale, float(drop_p),
                                          _ptr(keep),
                                          _ptr(rope[0]) if rope else 0, _ptr(rope[1]) if rope else 0, _ptr(qmeta),
-                                         _ptr(kmeta), sched.data_ptr(), _stream())
+                                         _ptr(kmeta), _stream())
         _lib.check(rc, "obt_attn_tc_bwd")
         return dqkv
     rc = _lib.load().obt_attn_simt_bwd(q, k, v, ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,

@@ -9,14 +9,6 @@ pytestmark = pytest.mark.gpu
 BF = torch.bfloat16
 
 
-@pytest.fixture(autouse=True, params=["0", "3"], ids=["bwd_per_item", "bwd_persistent"])
-def _backward_variant(request, monkeypatch):
-    """every test of this module runs with both forms of the backward kernels: one CTA per work item (legacy) and
-    persistent CTAs fetching items from a device counter (OBT_ATTN_PERSIST, csrc/attn_tc_bwd_persist.cu)"""
-    monkeypatch.setenv("OBT_ATTN_PERSIST", request.param)
-    yield
-
-
 def _ref(qkv, B, T, H, d, scale, mask4):
     C = H * d
     q, k, v = [t.view(B, T, H, d).transpose(1, 2).float() for t in qkv.float().split(C, dim=1)]
@@ -230,33 +222,3 @@ def test_tile_metadata_of_interval_masks():
                     bits |= 1 << it
             got = sum((int(kmeta[b, t, w]) & 0xffffffff) << (32 * w) for w in range(4))
             assert got == bits, (b, t, hex(got), hex(bits))
-
-
-@pytest.mark.parametrize("p_drop", [0.0, 0.1])
-def test_persistent_backward_many_items_per_cta_equals_per_item_kernels(p_drop, monkeypatch):
-    """More work items (B * H * T/128 = 512) than SMs: every persistent CTA runs several items back to back (barrier
-    phases, TMEM accumulators and the K/V / Q/dO rings carried across items). Same arithmetic in the same order per
-    item, so the result must equal the one-CTA-per-item kernels bit for bit."""
-    from omnibiote_b200 import ops
-    B, T, H, d = 8, 1024, 8, 128
-    C = H * d
-    g = torch.Generator(device="cuda").manual_seed(3)
-    qkv = torch.randn(B * T, 3 * C, generator=g, device="cuda").to(BF)
-    dy = (torch.randn(B * T, C, generator=g, device="cuda") * 0.1).to(BF)
-    ids = _doc_ids(B, T, 9)
-    ids[2, 900:] = 1
-    lo, hi = ops.doc_mask_intervals(ids, 3, True)
-    keep = ops.attn_keep_mask(B, H, T, p_drop, 7, 0, qkv.device) if p_drop > 0 else None
-    out = {}
-    for mode, spec in (("interval", ops.MaskSpec(None, B, H, T, lo, hi)), ("none", ops.MaskSpec(None, B, H, T))):
-        y, lse = ops.attention_fwd(qkv, B, T, H, d, 8.0 / C, spec, p_drop, keep, impl="tc")
-        for persist in ("0", "1", "2", "3"):
-            monkeypatch.setenv("OBT_ATTN_PERSIST", persist)
-            for rep in range(2):  # twice: the work counters must be back at zero after a launch
-                out[(mode, persist, rep)] = ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, 8.0 / C, spec, p_drop, keep,
-                                                              impl="tc")
-        for persist in ("1", "2", "3"):
-            for rep in range(2):
-                assert torch.equal(out[(mode, persist, rep)], out[(mode, "0", 0)]), (mode, persist, rep)
-    sched = ops._workspaces[("attn_sched", torch.int32, qkv.device)]
-    assert int(sched.abs().sum()) == 0
