@@ -64,7 +64,8 @@ struct AttnDqSmem {
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
 
-template <bool kDrop>
+// kPoly: a quarter of the exponentials of the interior path (element e with e % 4 == 3) on the FMA pipe (exp2_poly)
+template <bool kDrop, bool kPoly>
 __global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16* __restrict__ qkv, long long ld,
                   const __nv_bfloat16* __restrict__ dy, long long lddy, const AttnTcParams p, int C) {
@@ -319,7 +320,10 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
         // interior of a document for every row of the warp: no per-element interval tests
         const float nneg = -neg;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) ds[e] = fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nneg));
+        for (int e = 0; e < 32; ++e) {
+          const float x = fmaf(__uint_as_float(sv[e]), sc2, nneg);
+          ds[e] = (kPoly && (e & 3) == 3) ? exp2_poly(x) : fast_exp2(x);
+        }
       } else {
         // the 32 keys straddle an interval end for some row: per-row visibility bits, one bit test per element
         const uint32_t vm = row_ok ? interval_bits32(lo, hi, j0) : 0u;
@@ -429,7 +433,7 @@ struct AttnDkvSmem {
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
 
-template <bool kDrop>
+template <bool kDrop, bool kPoly>
 __global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_q64,
                    const __grid_constant__ CUtensorMap tm_dy64, const AttnTcParams p, int C) {
@@ -693,8 +697,9 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           for (int h2 = 0; h2 < 2; ++h2) {
             const float4 nd = nd4[e4 * 2 + h2];
             const int e = e4 * 4 + h2 * 2;
-            const float pr0 = fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nd.x));
-            const float pr1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), sc2, nd.z));
+            const float x0 = fmaf(__uint_as_float(sv[e]), sc2, nd.x), x1 = fmaf(__uint_as_float(sv[e + 1]), sc2, nd.z);
+            const float pr0 = fast_exp2(x0);
+            const float pr1 = (kPoly && h2 == 1) ? exp2_poly(x1) : fast_exp2(x1);  // e + 1 = 4 e4 + 3
             const bool kb0 = !kDrop || (kws[h2 * 2] & mybit), kb1 = !kDrop || (kws[h2 * 2 + 1] & mybit);
             ptw[e >> 1] = pack_bf16x2(kb0 ? pr0 : 0.f, kb1 ? pr1 : 0.f);
             dsw[e >> 1] = pack_bf16x2(pr0 * ((kb0 ? __uint_as_float(dv[e]) : 0.f) - nd.y),
@@ -925,30 +930,42 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
   p.dk = p.dq + C;
   p.dv = p.dq + 2 * C;
   p.ldd = ldd;
+  // OBT_ATTN_BWD_POLY=0 keeps every exponential on the MUFU (A/B runs)
+  const char* pe = getenv("OBT_ATTN_BWD_POLY");
+  const bool poly = !(pe != nullptr && pe[0] == '0');
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(attn_tc_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDqSmem::BYTES);
-    cudaError_t e2 = cudaFuncSetAttribute(attn_tc_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDkvSmem::BYTES);
-    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attn_tc_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDqSmem::BYTES);
-    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(attn_tc_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDkvSmem::BYTES);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
-      set_last_error("obt_attn_tc_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    cudaError_t e = cudaSuccess;
+    auto set = [&](auto kern, size_t bytes) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    };
+    set(attn_tc_dq_kernel<false, false>, AttnDqSmem::BYTES);
+    set(attn_tc_dq_kernel<true, false>, AttnDqSmem::BYTES);
+    set(attn_tc_dq_kernel<false, true>, AttnDqSmem::BYTES);
+    set(attn_tc_dq_kernel<true, true>, AttnDqSmem::BYTES);
+    set(attn_tc_dkv_kernel<false, false>, AttnDkvSmem::BYTES);
+    set(attn_tc_dkv_kernel<true, false>, AttnDkvSmem::BYTES);
+    set(attn_tc_dkv_kernel<false, true>, AttnDkvSmem::BYTES);
+    set(attn_tc_dkv_kernel<true, true>, AttnDkvSmem::BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("obt_attn_tc_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return OBT_ERR_CUDA;
     }
     attr_set = true;
   }
   dim3 grid((T + ATT_BM - 1) / ATT_BM, H, B);
-  if (drop_p > 0.f)
-    attn_tc_dq_kernel<true><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(
-        tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
-  else
-    attn_tc_dq_kernel<false><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(
-        tm_qkv, static_cast<const __nv_bfloat16*>(qkv), ld, static_cast<const __nv_bfloat16*>(dy), lddy, p, C);
+  auto qk = static_cast<const __nv_bfloat16*>(qkv);
+  auto dyp = static_cast<const __nv_bfloat16*>(dy);
+  const bool drop = drop_p > 0.f;
+  if (drop && poly) attn_tc_dq_kernel<true, true><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(tm_qkv, qk, ld, dyp, lddy, p, C);
+  else if (drop) attn_tc_dq_kernel<true, false><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(tm_qkv, qk, ld, dyp, lddy, p, C);
+  else if (poly) attn_tc_dq_kernel<false, true><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(tm_qkv, qk, ld, dyp, lddy, p, C);
+  else attn_tc_dq_kernel<false, false><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(tm_qkv, qk, ld, dyp, lddy, p, C);
   rc = check_launch("attn_tc_dq");
   if (rc) return rc;
-  if (drop_p > 0.f)
-    attn_tc_dkv_kernel<true><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
-  else
-    attn_tc_dkv_kernel<false><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
+  if (drop && poly) attn_tc_dkv_kernel<true, true><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
+  else if (drop) attn_tc_dkv_kernel<true, false><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
+  else if (poly) attn_tc_dkv_kernel<false, true><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
+  else attn_tc_dkv_kernel<false, false><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
   return check_launch("attn_tc_dkv");
 }

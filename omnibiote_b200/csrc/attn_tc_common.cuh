@@ -71,6 +71,22 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 2^x on the FMA / ALU pipes (Cody-Waite range reduction + degree-4 polynomial, relative error < 5e-5: far below the
+// bf16 rounding 2^-9 that follows): the forward kernel's softmax is co-limited by the MUFU (16 ex2 / clk / SM: 512
+// cycles per 64-key tile against 512 cycles of MMA), so a quarter of the exponentials is moved off it (the trick of
+// FlashAttention-4's softmax warps). x <= -126 (masked keys carry -inf) returns exactly 0.
+__device__ __forceinline__ float exp2_poly(float x) {
+  const float xc = fmaxf(x, -126.0f);
+  const float t = xc + 12582912.0f;            // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = xc - (t - 12582912.0f);      // fractional part in [-0.5, 0.5]
+  float p = fmaf(f, 0.0096181291f, 0.0555041087f);
+  p = fmaf(p, f, 0.2402265070f);
+  p = fmaf(p, f, 0.6931471806f);
+  p = fmaf(p, f, 1.0f);
+  const int r = __float_as_int(p) + (__float_as_int(t) << 23);  // exponent += integer part
+  return x > -126.0f ? __int_as_float(r) : 0.f;
+}
+
 // D[128 x 64] = A[128 x 128(d)] * B[64 x 128(d)]^T, both K-major; a tile = two 64-column sub-tiles `a_sub` /
 // `b_sub` bytes apart.
 __device__ __forceinline__ void issue_scores_128x64(uint32_t d_tmem, uint32_t a_addr, uint32_t a_sub, uint32_t b_addr,
