@@ -510,8 +510,16 @@ def run_b200(args):
     ops.PROFILE_GEMM = []
     ms_prof, _ = time_steps(trainer, dev_ids, 1, barrier)
     gemm_prof, ops.PROFILE_GEMM = ops.PROFILE_GEMM, None
-    g_flops = sum(f for f, _, _ in gemm_prof)
-    g_ms = sum(a.elapsed_time(b) for _, a, b in gemm_prof)
+    g_flops = sum(r[0] for r in gemm_prof)
+    g_ms = sum(r[1].elapsed_time(r[2]) for r in gemm_prof)
+    by_shape = {}
+    for f, a, b, label in gemm_prof:
+        e = by_shape.setdefault(label, [0, 0.0, 0.0])
+        e[0] += 1
+        e[1] += a.elapsed_time(b)
+        e[2] += f
+    gemm_by_shape = {k: {"launches": v[0], "ms": round(v[1], 3), "tflops": round(v[2] / (v[1] / 1e3) / 1e12, 1)}
+                     for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])}
 
     # ---- optional second device-resident measurement: the masked-rows-only head (same loss and gradients, the head
     # GEMMs / CE run on the ~15 % of rows inside the MLM mask). Reported under its own key, never as `value`: the
@@ -576,6 +584,9 @@ def run_b200(args):
             "peak_source": peak_src, "launches": len(gemm_prof),
             "measured_in": "one extra instrumented step after the timed region (CUDA events around every GEMM launch)",
             "share_of_step": g_ms / ms_prof if ms_prof > 0 else None,
+            # every distinct GEMM of the step (M x N x K, operand layouts N = K-major / T = MN-major, epilogue id):
+            # launches, summed CUDA-event time and TFLOP/s inside the step
+            "by_shape": gemm_by_shape,
             "step_model_flops_frac_of_2.25PF": value * ftok / world / 2.25e15,
             "step_model_flops_frac_of_measured_sustained": value * ftok / world / (peak_tf * 1e12),
         }

@@ -143,13 +143,17 @@ int obt_attn_tile_meta(const int* row_lo, const int* row_hi, int B, int T, int* 
  * delta_ready != 0, an INPUT already holding rowsum(dy * y) per head (obt_gemm_bf16 epilogue 11 emits it while
  * producing dy, and the pre-pass is skipped); autograd adjoint of model.py:111-148.
  * qmeta / kmeta: optional tile metadata (obt_attn_tile_meta).
+ * ds_scratch: optional bf16 [B*H * T * roundup(T,64)] scratch (128-byte aligned, contents irrelevant): when given, the
+ * dK/dV kernel also stores its dS^T tiles there and dQ = scale/(1-p) * dS K is accumulated from them by a score-free
+ * kernel (no second evaluation of Q K^T, dO V^T and the exponentials); NULL = the stand-alone dQ kernel.
  * rope_cos / rope_sin (optional, fp32 [>=T, 64]): when given, the adjoint of apply_rotary_emb is applied to dq and dk
  * in the kernels' epilogues (rope_sin = NULL: cosine scaling), so dqkv is the gradient of the PRE-rotary c_attn output. */
 int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, long long msb, long long msh, long long msq,
                     const int* row_lo, const int* row_hi, const void* y, long long ldy, const void* dy, long long lddy,
                     const float* lse, float* delta, int delta_ready, void* dqkv, long long ldd, int B, int H, int T,
                     int d, float scale, float drop_p, const unsigned int* keep, const float* rope_cos,
-                    const float* rope_sin, const int* qmeta, const unsigned int* kmeta, cudaStream_t stream);
+                    const float* rope_sin, const int* qmeta, const unsigned int* kmeta, void* ds_scratch,
+                    cudaStream_t stream);
 
 /* ---- attention-mask producers / compressors (input contract of the hot path) ------------------------------------
  * obt_doc_mask_intervals : per (b,i) visible key interval [lo,hi) from token ids = create_attention_mask

@@ -43,7 +43,7 @@ SIGNATURES = {
     "obt_attn_tc_fwd": (i32, [vp, i64, vp, i64, i64, i64, vp, vp, vp, i64, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp]),
     "obt_attn_tile_meta": (i32, [vp, vp, i32, i32, vp, vp, vp]),
     "obt_attn_tc_bwd": (i32, [vp, i64, vp, i64, i64, i64, vp, vp, vp, i64, vp, i64, vp, vp, i32, vp, i64, i32, i32, i32,
-                              i32, f32, f32, vp, vp, vp, vp, vp, vp]),
+                              i32, f32, f32, vp, vp, vp, vp, vp, vp, vp]),
     "obt_doc_mask_intervals": (i32, [vp, vp, vp, i32, i32, i64, i32, vp]),
     "obt_pad_mask_intervals": (i32, [vp, vp, vp, i32, i32, i64, vp]),
     "obt_mask_from_intervals": (i32, [vp, vp, vp, i32, i32, vp]),

@@ -39,8 +39,7 @@ struct AttnFwdSmem {
 constexpr int ATT_FWD_THREADS = 64 + 128;  // TMA warp, MMA warp, 4 softmax warps
 constexpr float ATT_LAZY_LOG2 = 8.0f;      // rescale O only when the row max grew by more than 2^8
 
-// kPoly: pairs 3 of every 4 (a quarter of the elements) take 2^x from exp2_poly instead of the MUFU
-template <bool kDrop, bool kPoly>
+template <bool kDrop>
 __global__ void __launch_bounds__(ATT_FWD_THREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                    const AttnTcParams p, int C) {
@@ -312,10 +311,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       uint32_t pk[32];
 #pragma unroll
       for (int e = 0; e < 64; e += 2) {
-        const float x0 = fmaf(s[e], mul, nm), x1 = fmaf(s[e + 1], mul, nm);
-        const bool poly = kPoly && ((e >> 1) & 3) == 3;  // compile-time after unrolling
-        const float p0 = poly ? exp2_poly(x0) : fast_exp2(x0);
-        const float p1 = poly ? exp2_poly(x1) : fast_exp2(x1);
+        const float p0 = fast_exp2(fmaf(s[e], mul, nm));
+        const float p1 = fast_exp2(fmaf(s[e + 1], mul, nm));
         lsum0 += p0;
         lsum1 += p1;
         pk[e >> 1] = pack_bf16x2(p0, p1);
@@ -422,14 +419,10 @@ extern "C" int obt_attn_tc_fwd(const void* qkv, long long ld, const void* mask, 
   p.nw = keep_words(T);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(attn_tc_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e1 = cudaFuncSetAttribute(attn_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           AttnFwdSmem::BYTES);
-    cudaError_t e2 = cudaFuncSetAttribute(attn_tc_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e2 = cudaFuncSetAttribute(attn_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           AttnFwdSmem::BYTES);
-    if (e1 == cudaSuccess)
-      e1 = cudaFuncSetAttribute(attn_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::BYTES);
-    if (e2 == cudaSuccess)
-      e2 = cudaFuncSetAttribute(attn_tc_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::BYTES);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
       set_last_error("obt_attn_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
       return OBT_ERR_CUDA;
@@ -437,15 +430,9 @@ extern "C" int obt_attn_tc_fwd(const void* qkv, long long ld, const void* mask, 
     attr_set = true;
   }
   dim3 grid((T + ATT_BM - 1) / ATT_BM, H, B);
-  // OBT_ATTN_FWD_POLY=0 keeps every exponential on the MUFU (A/B runs)
-  const char* pe = getenv("OBT_ATTN_FWD_POLY");
-  const bool poly = !(pe != nullptr && pe[0] == '0');
-  if (drop_p > 0.f) {
-    if (poly) attn_tc_fwd_kernel<true, true><<<grid, ATT_FWD_THREADS, AttnFwdSmem::BYTES, stream>>>(tm_q, tm_kv, p, C);
-    else attn_tc_fwd_kernel<true, false><<<grid, ATT_FWD_THREADS, AttnFwdSmem::BYTES, stream>>>(tm_q, tm_kv, p, C);
-  } else {
-    if (poly) attn_tc_fwd_kernel<false, true><<<grid, ATT_FWD_THREADS, AttnFwdSmem::BYTES, stream>>>(tm_q, tm_kv, p, C);
-    else attn_tc_fwd_kernel<false, false><<<grid, ATT_FWD_THREADS, AttnFwdSmem::BYTES, stream>>>(tm_q, tm_kv, p, C);
-  }
+  if (drop_p > 0.f)
+    attn_tc_fwd_kernel<true><<<grid, ATT_FWD_THREADS, AttnFwdSmem::BYTES, stream>>>(tm_q, tm_kv, p, C);
+  else
+    attn_tc_fwd_kernel<false><<<grid, ATT_FWD_THREADS, AttnFwdSmem::BYTES, stream>>>(tm_q, tm_kv, p, C);
   return check_launch("attn_tc_fwd");
 }

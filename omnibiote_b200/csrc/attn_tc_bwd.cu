@@ -64,8 +64,7 @@ struct AttnDqSmem {
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
 
-// kPoly: a quarter of the exponentials of the interior path (element e with e % 4 == 3) on the FMA pipe (exp2_poly)
-template <bool kDrop, bool kPoly>
+template <bool kDrop>
 __global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16* __restrict__ qkv, long long ld,
                   const __nv_bfloat16* __restrict__ dy, long long lddy, const AttnTcParams p, int C) {
@@ -320,10 +319,7 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat1
         // interior of a document for every row of the warp: no per-element interval tests
         const float nneg = -neg;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float x = fmaf(__uint_as_float(sv[e]), sc2, nneg);
-          ds[e] = (kPoly && (e & 3) == 3) ? exp2_poly(x) : fast_exp2(x);
-        }
+        for (int e = 0; e < 32; ++e) ds[e] = fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nneg));
       } else {
         // the 32 keys straddle an interval end for some row: per-row visibility bits, one bit test per element
         const uint32_t vm = row_ok ? interval_bits32(lo, hi, j0) : 0u;
@@ -433,7 +429,7 @@ struct AttnDkvSmem {
   static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
 };
 
-template <bool kDrop, bool kPoly>
+template <bool kDrop>
 __global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_q64,
                    const __grid_constant__ CUtensorMap tm_dy64, const AttnTcParams p, int C) {
@@ -649,6 +645,18 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       return it;
     };
 
+    // dS hand-over to the score-free dQ kernel: that kernel accumulates over 128-query tiles, so a 64-query sub-tile this
+    // CTA skips while its sibling is processed must read as zeros
+    __nv_bfloat16* ds_row = nullptr;
+    if (p.ds_out != nullptr && key_ok) ds_row = p.ds_out + (bh * T + j) * p.ds_pitch + hh * 32;
+    if (ds_row != nullptr) {
+      for (int z = 0; z < nq; ++z)
+        if (!relevant(z) && relevant(z ^ 1)) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) reinterpret_cast<uint4*>(ds_row + z * 64)[g] = make_uint4(0, 0, 0, 0);
+        }
+    }
+
     // two sub-tiles of look-ahead: the keep words come from HBM (written a whole forward pass earlier) and one
     // sub-tile of math (~1 us) did not cover that latency (11 % of the stall samples sat on the first use)
     int n = 0;
@@ -697,9 +705,8 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           for (int h2 = 0; h2 < 2; ++h2) {
             const float4 nd = nd4[e4 * 2 + h2];
             const int e = e4 * 4 + h2 * 2;
-            const float x0 = fmaf(__uint_as_float(sv[e]), sc2, nd.x), x1 = fmaf(__uint_as_float(sv[e + 1]), sc2, nd.z);
-            const float pr0 = fast_exp2(x0);
-            const float pr1 = (kPoly && h2 == 1) ? exp2_poly(x1) : fast_exp2(x1);  // e + 1 = 4 e4 + 3
+            const float pr0 = fast_exp2(fmaf(__uint_as_float(sv[e]), sc2, nd.x));
+            const float pr1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), sc2, nd.z));
             const bool kb0 = !kDrop || (kws[h2 * 2] & mybit), kb1 = !kDrop || (kws[h2 * 2 + 1] & mybit);
             ptw[e >> 1] = pack_bf16x2(kb0 ? pr0 : 0.f, kb1 ? pr1 : 0.f);
             dsw[e >> 1] = pack_bf16x2(pr0 * ((kb0 ? __uint_as_float(dv[e]) : 0.f) - nd.y),
@@ -785,6 +792,11 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           }
         }
       }
+      if (ds_row != nullptr) {  // dS^T[key j][queries i0 .. i0+31] for the score-free dQ kernel
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          reinterpret_cast<uint4*>(ds_row + it * 64)[g] = make_uint4(dsw[4 * g], dsw[4 * g + 1], dsw[4 * g + 2], dsw[4 * g + 3]);
+      }
       // P^T over the first 16 of the S^T columns this thread has read, dS^T over the first 16 of its dP^T columns
       __syncwarp();
       tmem_st_32x16(lane_addr + st * 128 + hh * 32, ptw);
@@ -862,6 +874,176 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
 }
 
+
+// =============================================================================================
+// Score-free dQ kernel (round 2). The dK/dV kernel computes every dS^T tile anyway (as bf16, for dK += dS^T Q); when it
+// also stores them (AttnTcParams::ds_out), dQ = scale / (1-p) * dS K needs neither the score products S = Q K^T and
+// dP = dO V^T nor the exponentials a second time: per 64 keys ONE 128 x 128 x 64 product instead of three, no MUFU, no
+// per-row parameters, 128 TMEM columns and 96 KB of shared memory, so two CTAs share an SM and hide each other's
+// prologue / epilogue. The price is the round trip of the visited dS tiles through L2 / HBM (2 bytes per score).
+//   A = dS[128 queries x 64 keys]: the stored dS^T tile [64 keys][128 queries] read as an MN-major operand (two
+//       64-query halves 8 KB apart); B = K[64 keys x 128 d] read MN-major like in the dQ += dS K product above.
+// A 128-key tile is visited iff the dK/dV kernel wrote it: relevance bit of either 64-query half of this query tile.
+// =============================================================================================
+constexpr int ATT_DQ2_STAGES = 3;
+constexpr int ATT_DQ2_THREADS = 64 + 128;  // TMA warp, MMA warp, 4 epilogue warps (one thread per query row)
+
+struct AttnDq2Smem {
+  static constexpr uint32_t A_OFF = 0;                                      // dS^T sub-tiles [64 keys x 128 queries]
+  static constexpr uint32_t B_OFF = A_OFF + ATT_DQ2_STAGES * ATT_SUB_BYTES;  // K sub-tiles [64 keys x 128 d]
+  static constexpr uint32_t BAR_OFF = B_OFF + ATT_DQ2_STAGES * ATT_SUB_BYTES;
+  static constexpr uint32_t BYTES = BAR_OFF + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(ATT_DQ2_THREADS, 2)
+attn_tc_dq2_kernel(const __grid_constant__ CUtensorMap tm_ds, const __grid_constant__ CUtensorMap tm_k64,
+                   const AttnTcParams p, int C) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  uint8_t* sA = smem + AttnDq2Smem::A_OFF;
+  uint8_t* sB = smem + AttnDq2Smem::B_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnDq2Smem::BAR_OFF);
+  uint64_t* full = bars + 0;    // [3]
+  uint64_t* empty = bars + 3;   // [3]
+  uint64_t* done = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tq = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int T = p.T;
+  const int nT = gridDim.x;
+  const int t0 = tq * ATT_BM;
+  // which 128-key tiles the dK/dV kernel visited for either 64-query half of this tile (bit kt)
+  uint32_t visit = 0;
+  for (int kt = 0; kt < nT; ++kt) {
+    bool v = true;
+    if (p.kmeta != nullptr) {
+      const unsigned int* km = p.kmeta + (static_cast<long long>(b) * nT + kt) * 4;
+      const int s0 = 2 * tq, s1 = 2 * tq + 1;
+      v = ((km[s0 >> 5] >> (s0 & 31)) & 1u) || ((km[s1 >> 5] >> (s1 & 31)) & 1u);
+    }
+    if (v) visit |= 1u << kt;
+  }
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_ds);
+    tma_prefetch_desc(&tm_k64);
+    for (int i = 0; i < ATT_DQ2_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(tmem_slot), 0);
+  const int n_sub = 2 * __popc(visit);  // 64-key sub-tiles
+  const int row0 = b * T;
+  const int bh = b * p.H + h;
+  const int kcol = C + h * ATT_D;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int kt = 0; kt < nT; ++kt) {
+        if (!((visit >> kt) & 1u)) continue;
+#pragma unroll 1
+        for (int hs = 0; hs < 2; ++hs) {
+          const int key0 = kt * ATT_BN + hs * 64;
+          mbar_wait(&empty[st], ph ^ 1);
+          mbar_expect_tx(&full[st], 2 * ATT_SUB_BYTES);
+          // dS^T rows key0.. (zero-filled beyond T keys), queries t0..t0+127 as two 64-wide halves
+          tma_load_3d(&tm_ds, &full[st], sA + st * ATT_SUB_BYTES, t0, key0, bh);
+          tma_load_3d(&tm_ds, &full[st], sA + st * ATT_SUB_BYTES + 8192, t0 + 64, key0, bh);
+          tma_load_2d(&tm_k64, &full[st], sB + st * ATT_SUB_BYTES, kcol, row0 + key0);
+          tma_load_2d(&tm_k64, &full[st], sB + st * ATT_SUB_BYTES + 8192, kcol + 64, row0 + key0);
+          if (++st == ATT_DQ2_STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    const int n_sub_u = __shfl_sync(0xffffffffu, n_sub, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(128, 128, true, true);
+    for (int s = 0; s < n_sub_u; ++s) {
+      const int st = s % ATT_DQ2_STAGES;
+      mbar_wait(&full[st], (s / ATT_DQ2_STAGES) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t a_addr = smem_u32(sA + st * ATT_SUB_BYTES), b_addr = smem_u32(sB + st * ATT_SUB_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t a_desc = make_smem_desc_sw128(a_addr + kk * 2048, 8192, 1024);
+          const uint64_t b_desc = make_smem_desc_sw128(b_addr + kk * 2048, 8192, 1024);
+          umma_bf16_ss<1>(tmem_base, a_desc, b_desc, idesc, (s > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[st]);
+        if (s == n_sub_u - 1) umma_commit(done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue: one thread per query row; dq = scale / (1-p) * acc, rotary adjoint, bf16
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int i = t0 + r;
+    const bool row_ok = i < T;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float oscale = p.scale * (p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f);
+    const bool do_rope = row_ok && p.rope_cos != nullptr;
+    __nv_bfloat16* drow = p.dq + (static_cast<long long>(row0) + i) * p.ldd + h * ATT_D;
+    if (n_sub > 0) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      __syncwarp();
+      if (n_sub > 0) {
+        tmem_ld_32x32(lane_addr + c * 32, o);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[e] = 0u;
+      }
+      if (row_ok) {
+        float f[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(o[e]) * oscale;
+        if (do_rope) {
+          const long long toff = static_cast<long long>(i) * (ATT_D / 2) + c * 16;
+          float4 rcs[4], rsn[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            rcs[g] = reinterpret_cast<const float4*>(p.rope_cos + toff)[g];
+            rsn[g] = p.rope_sin ? reinterpret_cast<const float4*>(p.rope_sin + toff)[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int e = 0; e < 32; ++e) f[e] = rb(f[e]);
+          rope_adjoint32(f, rcs, rsn, p.rope_sin != nullptr);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          reinterpret_cast<uint4*>(drow + c * 32)[g] =
+              make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
+                         pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<1>(tmem_base, 128);
+  }
+}
+
 }  // namespace obt
 
 using namespace obt;
@@ -879,7 +1061,7 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
                                const void* dy, long long lddy, const float* lse, float* delta, int delta_ready,
                                void* dqkv, long long ldd, int B, int H, int T, int d, float scale, float drop_p,
                                const unsigned int* keep, const float* rope_cos, const float* rope_sin,
-                               const int* qmeta, const unsigned int* kmeta, cudaStream_t stream) {
+                               const int* qmeta, const unsigned int* kmeta, void* ds_scratch, cudaStream_t stream) {
   OBT_REQUIRE(qkv && y && dy && lse && delta && dqkv, "obt_attn_tc_bwd: null pointer");
   OBT_REQUIRE((reinterpret_cast<uintptr_t>(rope_cos) & 15) == 0 && (reinterpret_cast<uintptr_t>(rope_sin) & 15) == 0,
               "obt_attn_tc_bwd: rotary tables must be 16-byte aligned");
@@ -930,23 +1112,17 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
   p.dk = p.dq + C;
   p.dv = p.dq + 2 * C;
   p.ldd = ldd;
-  // OBT_ATTN_BWD_POLY=0 keeps every exponential on the MUFU (A/B runs)
-  const char* pe = getenv("OBT_ATTN_BWD_POLY");
-  const bool poly = !(pe != nullptr && pe[0] == '0');
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaSuccess;
     auto set = [&](auto kern, size_t bytes) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
     };
-    set(attn_tc_dq_kernel<false, false>, AttnDqSmem::BYTES);
-    set(attn_tc_dq_kernel<true, false>, AttnDqSmem::BYTES);
-    set(attn_tc_dq_kernel<false, true>, AttnDqSmem::BYTES);
-    set(attn_tc_dq_kernel<true, true>, AttnDqSmem::BYTES);
-    set(attn_tc_dkv_kernel<false, false>, AttnDkvSmem::BYTES);
-    set(attn_tc_dkv_kernel<true, false>, AttnDkvSmem::BYTES);
-    set(attn_tc_dkv_kernel<false, true>, AttnDkvSmem::BYTES);
-    set(attn_tc_dkv_kernel<true, true>, AttnDkvSmem::BYTES);
+    set(attn_tc_dq_kernel<false>, AttnDqSmem::BYTES);
+    set(attn_tc_dq_kernel<true>, AttnDqSmem::BYTES);
+    set(attn_tc_dkv_kernel<false>, AttnDkvSmem::BYTES);
+    set(attn_tc_dkv_kernel<true>, AttnDkvSmem::BYTES);
+    set(attn_tc_dq2_kernel, AttnDq2Smem::BYTES);
     if (e != cudaSuccess) {
       set_last_error("obt_attn_tc_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return OBT_ERR_CUDA;
@@ -954,18 +1130,37 @@ extern "C" int obt_attn_tc_bwd(const void* qkv, long long ld, const void* mask, 
     attr_set = true;
   }
   dim3 grid((T + ATT_BM - 1) / ATT_BM, H, B);
-  auto qk = static_cast<const __nv_bfloat16*>(qkv);
-  auto dyp = static_cast<const __nv_bfloat16*>(dy);
   const bool drop = drop_p > 0.f;
-  if (drop && poly) attn_tc_dq_kernel<true, true><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(tm_qkv, qk, ld, dyp, lddy, p, C);
-  else if (drop) attn_tc_dq_kernel<true, false><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(tm_qkv, qk, ld, dyp, lddy, p, C);
-  else if (poly) attn_tc_dq_kernel<false, true><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(tm_qkv, qk, ld, dyp, lddy, p, C);
-  else attn_tc_dq_kernel<false, false><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(tm_qkv, qk, ld, dyp, lddy, p, C);
-  rc = check_launch("attn_tc_dq");
-  if (rc) return rc;
-  if (drop && poly) attn_tc_dkv_kernel<true, true><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
-  else if (drop) attn_tc_dkv_kernel<true, false><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
-  else if (poly) attn_tc_dkv_kernel<false, true><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
-  else attn_tc_dkv_kernel<false, false><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
+  // dS hand-over (ds_scratch given): the dK/dV kernel stores its dS^T tiles, a score-free kernel turns them into dQ
+  const long long ds_pitch = (static_cast<long long>(T) + 63) / 64 * 64;
+  // the score-free kernel must visit exactly the tiles the dK/dV kernel wrote: it needs the same relevance bits (tile
+  // metadata) whenever an interval mask is in use, and keeps its visit set in one 32-bit word (T <= 4096)
+  if (ds_scratch != nullptr && ((p.row_lo != nullptr && p.kmeta == nullptr) || T > 32 * ATT_BN)) ds_scratch = nullptr;
+  if (ds_scratch != nullptr) {
+    OBT_REQUIRE((reinterpret_cast<uintptr_t>(ds_scratch) & 127) == 0, "obt_attn_tc_bwd: ds_scratch must be 128-byte aligned");
+    p.ds_out = static_cast<__nv_bfloat16*>(ds_scratch);
+    p.ds_pitch = ds_pitch;
+  } else {
+    auto qk = static_cast<const __nv_bfloat16*>(qkv);
+    auto dyp = static_cast<const __nv_bfloat16*>(dy);
+    if (drop) attn_tc_dq_kernel<true><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(tm_qkv, qk, ld, dyp, lddy, p, C);
+    else attn_tc_dq_kernel<false><<<grid, ATT_BWD_THREADS, AttnDqSmem::BYTES, stream>>>(tm_qkv, qk, ld, dyp, lddy, p, C);
+    rc = check_launch("attn_tc_dq");
+    if (rc) return rc;
+  }
+  if (drop) attn_tc_dkv_kernel<true><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
+  else attn_tc_dkv_kernel<false><<<grid, ATT_BWD_THREADS, AttnDkvSmem::BYTES, stream>>>(tm_qkv, tm_q64, tm_dy64, p, C);
+  if (ds_scratch != nullptr) {
+    rc = check_launch("attn_tc_dkv");
+    if (rc) return rc;
+    CUtensorMap tm_ds;
+    // [B*H][T keys][ds_pitch queries]: queries contiguous; keys beyond T read as zeros (per (batch, head) slab)
+    rc = get_tensor_map_3d(&tm_ds, ds_scratch, static_cast<uint64_t>(ds_pitch), static_cast<uint64_t>(T),
+                           static_cast<uint64_t>(B) * H, static_cast<uint64_t>(ds_pitch),
+                           static_cast<uint64_t>(ds_pitch) * T, 64, 64, 1);
+    if (rc) return rc;
+    attn_tc_dq2_kernel<<<grid, ATT_DQ2_THREADS, AttnDq2Smem::BYTES, stream>>>(tm_ds, tm_q64, p, C);
+    return check_launch("attn_tc_dq2");
+  }
   return check_launch("attn_tc_dkv");
 }

@@ -36,6 +36,10 @@ struct AttnTcParams {
   __nv_bfloat16* dk;
   __nv_bfloat16* dv;
   long long ldd;
+  // optional dS hand-over (round 2): the dK/dV kernel also stores its dS^T tiles (bf16 [B*H][T keys][ds_pitch queries],
+  // ds_pitch = T rounded up to 64) and a score-free dQ kernel (attn_tc_dq2_kernel) accumulates dQ = dS K from them
+  __nv_bfloat16* ds_out;
+  long long ds_pitch;
   // optional adjoint of the rotary embedding on dq / dk (fp32 tables [>= T, 64]; sin == nullptr: cosine scaling)
   const float* rope_cos;
   const float* rope_sin;
@@ -71,21 +75,10 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// 2^x on the FMA / ALU pipes (Cody-Waite range reduction + degree-4 polynomial, relative error < 5e-5: far below the
-// bf16 rounding 2^-9 that follows): the forward kernel's softmax is co-limited by the MUFU (16 ex2 / clk / SM: 512
-// cycles per 64-key tile against 512 cycles of MMA), so a quarter of the exponentials is moved off it (the trick of
-// FlashAttention-4's softmax warps). x <= -126 (masked keys carry -inf) returns exactly 0.
-__device__ __forceinline__ float exp2_poly(float x) {
-  const float xc = fmaxf(x, -126.0f);
-  const float t = xc + 12582912.0f;            // 1.5 * 2^23: the integer part lands in the low mantissa bits
-  const float f = xc - (t - 12582912.0f);      // fractional part in [-0.5, 0.5]
-  float p = fmaf(f, 0.0096181291f, 0.0555041087f);
-  p = fmaf(p, f, 0.2402265070f);
-  p = fmaf(p, f, 0.6931471806f);
-  p = fmaf(p, f, 1.0f);
-  const int r = __float_as_int(p) + (__float_as_int(t) << 23);  // exponent += integer part
-  return x > -126.0f ? __int_as_float(r) : 0.f;
-}
+// Measured and rejected (round 2, profiles/r02e_attn_probe_poly_{on,off}.txt): a quarter of the exponentials on the
+// FMA / ALU pipes (Cody-Waite range reduction + degree-4 polynomial, relative error 5.6e-5) instead of the MUFU, the
+// FlashAttention-4 trick: forward 130.7 -> 139.9 us, dQ 212.3 -> 216.0 us, dK/dV 259.2 -> 267.1 us. The ~9 extra issue
+// slots per converted element cost more than the MUFU slot they free: none of the three kernels is MUFU-bound.
 
 // D[128 x 64] = A[128 x 128(d)] * B[64 x 128(d)]^T, both K-major; a tile = two 64-column sub-tiles `a_sub` /
 // `b_sub` bytes apart.

@@ -24,6 +24,9 @@ ATTN_IMPL = _os.environ.get("OBT_ATTN_IMPL", "auto")
 # delta = rowsum(dO * O) of the attention backward from the epilogue of the GEMM that produces dO (EPI_DELTA) instead of
 # a separate memory-bound pass; OBT_FUSE_ATTN_DELTA=0 restores the stand-alone kernel (A/B runs, tests)
 FUSE_ATTN_DELTA = _os.environ.get("OBT_FUSE_ATTN_DELTA", "1") != "0"
+# attention backward: the dK/dV kernel hands its dS tiles to a score-free dQ kernel through a bf16 scratch instead of a
+# second evaluation of the scores and exponentials in a stand-alone dQ kernel; OBT_ATTN_DS_HANDOVER=0 = stand-alone dQ
+ATTN_DS_HANDOVER = _os.environ.get("OBT_ATTN_DS_HANDOVER", "1") != "0"
 
 _workspaces: dict = {}
 
@@ -136,7 +139,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, a
     _lib.check(rc, "obt_gemm_bf16")
     if prof is not None:
         ev1.record()
-        prof.append((2.0 * M * N * K, ev0, ev1))
+        prof.append((2.0 * M * N * K, ev0, ev1, f"{M}x{N}x{K} {'T' if a_mn else 'N'}{'T' if b_mn else 'N'} epi{epilogue}"))
     return out
 
 
@@ -403,13 +406,16 @@ def attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, mask: MaskSpec, drop_p, ke
         impl = "tc" if d == 128 else "simt"
     if impl == "tc":
         qmeta, kmeta = mask.tile_meta() if use_iv else (None, None)
+        ds_scratch = None
+        if ATTN_DS_HANDOVER:
+            ds_scratch = workspace("attn_ds", B * H * T * ((T + 63) // 64 * 64), torch.bfloat16, qkv.device)
         rc = _lib.load().obt_attn_tc_bwd(qkv.data_ptr(), ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,
                                          _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0,
                                          y.data_ptr(), C, dy.data_ptr(), lddy, lse.data_ptr(), delta.data_ptr(),
                                          int(delta_ready), dqkv.data_ptr(), 3 * C, B, H, T, d, scale, float(drop_p),
                                          _ptr(keep),
                                          _ptr(rope[0]) if rope else 0, _ptr(rope[1]) if rope else 0, _ptr(qmeta),
-                                         _ptr(kmeta), _stream())
+                                         _ptr(kmeta), _ptr(ds_scratch), _stream())
         _lib.check(rc, "obt_attn_tc_bwd")
         return dqkv
     rc = _lib.load().obt_attn_simt_bwd(q, k, v, ld, _ptr(mask.tensor), mask.msb, mask.msh, mask.msq,

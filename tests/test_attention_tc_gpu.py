@@ -9,6 +9,15 @@ pytestmark = pytest.mark.gpu
 BF = torch.bfloat16
 
 
+@pytest.fixture(autouse=True, params=[False, True], ids=["dq_standalone", "dq_from_ds_handover"])
+def _backward_variant(request, monkeypatch):
+    """every test of this module runs with both backward schedules: stand-alone dQ kernel (re-evaluates the scores), and
+    the dK/dV kernel handing its dS tiles to the score-free dQ kernel (ops.ATTN_DS_HANDOVER, the default)"""
+    from omnibiote_b200 import ops
+    monkeypatch.setattr(ops, "ATTN_DS_HANDOVER", request.param)
+    yield
+
+
 def _ref(qkv, B, T, H, d, scale, mask4):
     C = H * d
     q, k, v = [t.view(B, T, H, d).transpose(1, 2).float() for t in qkv.float().split(C, dim=1)]
