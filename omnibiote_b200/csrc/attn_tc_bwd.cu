@@ -652,8 +652,9 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     if (ds_row != nullptr) {
       for (int z = 0; z < nq; ++z)
         if (!relevant(z) && relevant(z ^ 1)) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) reinterpret_cast<uint4*>(ds_row + z * 64)[g] = make_uint4(0, 0, 0, 0);
+          const uint32_t zero8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          st_global_256(ds_row + z * 64, zero8);
+          st_global_256(ds_row + z * 64 + 16, zero8);
         }
     }
 
@@ -792,10 +793,14 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           }
         }
       }
-      if (ds_row != nullptr) {  // dS^T[key j][queries i0 .. i0+31] for the score-free dQ kernel
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          reinterpret_cast<uint4*>(ds_row + it * 64)[g] = make_uint4(dsw[4 * g], dsw[4 * g + 1], dsw[4 * g + 2], dsw[4 * g + 3]);
+      if (ds_row != nullptr) {
+        // dS^T[key j][queries i0 .. i0+31] for the score-free dQ kernel: the lanes of a warp write 32 different rows, so
+        // two 256-bit stores (one full sector each) instead of four 128-bit ones halve the LSU transactions - with the
+        // latter the stores cost this kernel 75 us (264 -> 339 us, profiles/r02f_attn_probe_launches_ds*.txt)
+        const uint32_t lo8[8] = {dsw[0], dsw[1], dsw[2], dsw[3], dsw[4], dsw[5], dsw[6], dsw[7]};
+        const uint32_t hi8[8] = {dsw[8], dsw[9], dsw[10], dsw[11], dsw[12], dsw[13], dsw[14], dsw[15]};
+        st_global_256(ds_row + it * 64, lo8);
+        st_global_256(ds_row + it * 64 + 16, hi8);
       }
       // P^T over the first 16 of the S^T columns this thread has read, dS^T over the first 16 of its dP^T columns
       __syncwarp();

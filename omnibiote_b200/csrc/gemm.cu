@@ -245,7 +245,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int chalf = ew >> 2;     // which 128-column half this warp stores
     uint8_t* stage = epi_stage + ew * GEMM_STAGE_BYTES_PER_WARP;
     int it = 0;
+    // second-operand slice of a tile -> L2, one tile ahead of its use (see epilogue_prefetch_aux)
+    auto prefetch_tile = [&](int t) {
+      if (t >= total_tiles) return;
+      const TileCoord tp = tile_coord(t, p.num_m, p.num_n);
+      const long long rb = static_cast<long long>(tp.m_blk) * (GEMM_BM_CTA * kCluster) + cta_rank * GEMM_BM_CTA + q * 32;
+      epilogue_prefetch_aux(p, rb + lane, tp.n_blk * GEMM_BN + chalf * 128);
+    };
+    prefetch_tile(cluster_id);
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+      prefetch_tile(tile + num_clusters);
       const TileCoord tc = tile_coord(tile, p.num_m, p.num_n);
       const int acc_stage = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;

@@ -355,6 +355,17 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
       const int gcol = col_base + seg * 8;
       const bool col_ok = gcol < p.N;
       const bool vec = p.vec_ok && (p.N - gcol >= 8);
+      // second operand of all 8 row-iterations first: 8 independent 16-byte loads in flight per lane (they are the
+      // epilogue's only long-latency accesses; with 4 at a time the K = 1024 GEMMs were bound by their latency)
+      uint4 axs[8];
+      if constexpr (EpiTraits<EPI>::kAuxIn) {
+#pragma unroll
+        for (int it8 = 0; it8 < 8; ++it8) {
+          const long long grow = row_base + it8 * 4 + rsub;
+          axs[it8] = make_uint4(0, 0, 0, 0);
+          if (vec && grow < p.M) axs[it8] = *reinterpret_cast<const uint4*>(p.aux_in + grow * p.ld_aux_in + gcol);
+        }
+      }
       // two groups of 4 row-iterations (keeps the unrolled code of each epilogue variant within the I-cache)
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {
@@ -375,11 +386,7 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
               if (p.rope_sin != nullptr) rs[it] = *reinterpret_cast<const float4*>(p.rope_sin + off);
             }
           }
-          if constexpr (EpiTraits<EPI>::kAuxIn) {
-            const long long grow = row_base + rl;
-            ax[it] = make_uint4(0, 0, 0, 0);
-            if (vec && grow < p.M) ax[it] = *reinterpret_cast<const uint4*>(p.aux_in + grow * p.ld_aux_in + gcol);
-          }
+          if constexpr (EpiTraits<EPI>::kAuxIn) ax[it] = hf == 0 ? axs[it] : axs[4 + it];
         }
         // ... then the math and the stores
 #pragma unroll
@@ -438,6 +445,21 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
       }
     }
   }
+}
+
+// L2 prefetch of the aux_in slice an epilogue warp will read for a tile: rows row_base + lane (32 rows), 128 columns from
+// column col0 (256 bytes = two 128-byte lines per row). Issued one tile AHEAD: the in-step per-shape table
+// (profiles/r02e_bench_n1.json, roofline.by_shape) showed every GEMM whose epilogue reads a second operand (residual,
+// GELU derivative, y for delta) far below the plain ones - 610 / 700 TFLOP/s at K = 1024 against ~1590 for the head -
+// because those reads are cold HBM accesses issued only after the tile's main loop, four 16-byte loads per thread at
+// a time: latency-bound. With the lines already in L2 the same loads cost a third of the latency.
+__device__ __forceinline__ void epilogue_prefetch_aux(const GemmParams& p, long long row, int col0) {
+  const bool has_aux = (p.epi == EPI_RESID || p.epi == EPI_GELU_BWD || p.epi == EPI_RESID_DROPOUT || p.epi == EPI_MUL ||
+                        p.epi == EPI_DELTA);
+  if (!has_aux || row >= p.M || col0 >= p.N) return;
+  const char* a = reinterpret_cast<const char*>(p.aux_in + row * p.ld_aux_in + col0);
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+  if (col0 + 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
 }
 
 // Whole accumulator slice of one epilogue warp: rows row_base..row_base+31 (TMEM lanes of this warp's quadrant),

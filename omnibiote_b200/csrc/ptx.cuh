@@ -335,6 +335,14 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
                : "memory");
 }
 
+// 256-bit global store (sm_100: STG.E.256; the address must be 32-byte aligned): one full 32-byte sector per lane and
+// instruction instead of two half-filled ones with 128-bit stores when the lanes of a warp write different rows.
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // misc numeric helpers
 // ---------------------------------------------------------------------------------------------
