@@ -11,6 +11,7 @@
 //                                 -> swizzled smem transpose -> fused epilogue -> coalesced 16-byte global stores
 // Operand layouts: either operand may be K-major (K contiguous in memory) or MN-major (M/N contiguous), which covers
 // forward (K,K), dgrad (K,MN) and wgrad (MN,MN) without materialising transposes.
+#include <math.h>
 #include "common.cuh"
 #include "ptx.cuh"
 #include "gemm_epilogue.cuh"
@@ -431,6 +432,7 @@ extern "C" int obt_gemm_bf16(const void* A, const void* B, void* D, long long M,
   p.aux_out = static_cast<__nv_bfloat16*>(aux_out);
   p.ld_aux_out = ld_aux_out;
   p.drop_p = drop_p;
+  p.drop_thr = static_cast<uint32_t>(ceilf(drop_p * 16777216.0f));
   p.seed = seed;
   p.offset = offset;
   p.rope_cos = rope_cos;

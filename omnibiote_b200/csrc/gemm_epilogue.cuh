@@ -49,6 +49,7 @@ struct GemmParams {
   long long ld_aux_out;
   float* partial;
   float drop_p;
+  uint32_t drop_thr;  // ceil(drop_p * 2^24): keep <=> (r >> 8) >= drop_thr
   unsigned long long seed, offset;
   // EPI_ROPE: fp32 tables [rope_T rows, rope_d / 2]; rope_sin == nullptr -> cosine scaling (real bf16 freqs_cis)
   const float* rope_cos;
@@ -209,8 +210,8 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, float (&v)[8]
       const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float u01 = (rr[e] >> 8) * (1.0f / 16777216.0f);
-        const float d = (u01 >= p.drop_p) ? rb(v[4 * j4 + e] * scale) : 0.f;
+        // keep <=> (r >> 8) * 2^-24 >= p <=> (r >> 8) >= ceil(p * 2^24): exact on both sides, one integer compare
+        const float d = ((rr[e] >> 8) >= p.drop_thr) ? rb(v[4 * j4 + e] * scale) : 0.f;
         v[4 * j4 + e] = a[4 * j4 + e] + d;
       }
     }
@@ -335,6 +336,21 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
   for (int c = c_begin; c < c_end; ++c) {
     const int col_base = n0 + c * 64;
     if (col_base >= p.N) break;  // warp-uniform
+    // second operand of all 8 row-iterations FIRST: 8 independent 16-byte loads in flight per lane, issued before the
+    // accumulator read-out so that their (L2) latency overlaps the tcgen05.ld and the smem staging. They are the
+    // epilogue's only long-latency accesses; issued after the staging, four at a time, they made every K = 1024 GEMM
+    // with a second operand epilogue-bound (profiles/r02e_bench_n1.json: 610 / 700 TFLOP/s against ~1590 for the head).
+    const int gcol_a = col_base + seg * 8;
+    const bool vec_a = p.vec_ok && (p.N - gcol_a >= 8);
+    uint4 axs[8];
+    if constexpr (EpiTraits<EPI>::kAuxIn) {
+#pragma unroll
+      for (int it8 = 0; it8 < 8; ++it8) {
+        const long long grow = row_base + it8 * 4 + rsub;
+        axs[it8] = make_uint4(0, 0, 0, 0);
+        if (vec_a && grow < p.M) axs[it8] = *reinterpret_cast<const uint4*>(p.aux_in + grow * p.ld_aux_in + gcol_a);
+      }
+    }
     uint32_t r0[32], r1[32];
     __syncwarp();
     tmem_ld_32x32(taddr + c * 64, r0);
@@ -355,17 +371,6 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
       const int gcol = col_base + seg * 8;
       const bool col_ok = gcol < p.N;
       const bool vec = p.vec_ok && (p.N - gcol >= 8);
-      // second operand of all 8 row-iterations first: 8 independent 16-byte loads in flight per lane (they are the
-      // epilogue's only long-latency accesses; with 4 at a time the K = 1024 GEMMs were bound by their latency)
-      uint4 axs[8];
-      if constexpr (EpiTraits<EPI>::kAuxIn) {
-#pragma unroll
-        for (int it8 = 0; it8 < 8; ++it8) {
-          const long long grow = row_base + it8 * 4 + rsub;
-          axs[it8] = make_uint4(0, 0, 0, 0);
-          if (vec && grow < p.M) axs[it8] = *reinterpret_cast<const uint4*>(p.aux_in + grow * p.ld_aux_in + gcol);
-        }
-      }
       // two groups of 4 row-iterations (keeps the unrolled code of each epilogue variant within the I-cache)
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {
