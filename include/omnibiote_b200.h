@@ -113,8 +113,10 @@ int obt_pool_bwd(const void* emb, const void* pooled, const void* dout, void* de
  * Attention dropout (dropout_p of model.py:118,134) is a precomputed bit matrix keep[B,H,T,ceil(T/32)] drawn ONCE
  * per layer and micro-batch by obt_attn_keep_mask from (seed, offset) and only read by the forward and backward
  * kernels (key j of query (b,h,i): word j/32, bit 8*(j&3) + 7 - ((j&31)>>2)); keep may be NULL when drop_p == 0. */
+/* row_lo / row_hi (optional, int32 [B,T]): the interval mask the kernels will use; words of a row entirely outside its
+ * visible interval are then stored as all-ones instead of being drawn (they only ever multiply zero probabilities). */
 int obt_attn_keep_mask(unsigned int* keep, int B, int H, int T, float drop_p, unsigned long long seed,
-                       unsigned long long offset, cudaStream_t stream);
+                       unsigned long long offset, const int* row_lo, const int* row_hi, cudaStream_t stream);
 int obt_attn_simt_fwd(const void* q, const void* k, const void* v, long long ld, const void* mask, long long msb,
                       long long msh, long long msq, const int* row_lo, const int* row_hi, void* y, long long ldy,
                       float* lse, int B, int H, int T, int d, float scale, float drop_p, const unsigned int* keep,

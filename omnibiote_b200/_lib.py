@@ -35,7 +35,7 @@ SIGNATURES = {
     "obt_pool_splits": (i32, [i32]),
     "obt_pool": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
     "obt_pool_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
-    "obt_attn_keep_mask": (i32, [vp, i32, i32, i32, f32, u64, u64, vp]),
+    "obt_attn_keep_mask": (i32, [vp, i32, i32, i32, f32, u64, u64, vp, vp, vp]),
     "obt_attn_simt_fwd": (i32, [vp, vp, vp, i64, vp, i64, i64, i64, vp, vp, vp, i64, vp, i32, i32, i32, i32, f32, f32,
                                 vp, vp]),
     "obt_attn_simt_bwd": (i32, [vp, vp, vp, i64, vp, i64, i64, i64, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, i64,

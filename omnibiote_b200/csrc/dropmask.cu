@@ -8,6 +8,7 @@
 // 1/(1-p) scaling uses the caller's p. The stream is counter based: (seed, offset, flat word index).
 #include "common.cuh"
 #include "dropmask.cuh"
+#include "ptx.cuh"
 
 namespace obt {
 
@@ -38,17 +39,50 @@ __device__ __forceinline__ uint32_t keep_word_draw(uint32_t k0, uint32_t k1, uns
   return ~lt;  // keep <=> u >= thr
 }
 
-// grid.x covers the B*H*T*nw words, 8 consecutive words (256 keys of one query row) per thread
+// grid.x covers the B*H*T*nw words, 8 consecutive words (256 keys of one query row) per thread.
+// With an interval mask (row_lo / row_hi, int32 [B,T]) the words of a row that lie entirely outside its visible interval
+// are not drawn but stored as all-ones: every consumer multiplies those bits with an exactly-zero probability, and with
+// packed documents they are ~60 % of the matrix (the kernel is ALU-bound). Fully-masked rows (lo >= hi) attend to
+// every key and are drawn completely. kByRows (nw % 8 == 0): the 32 lanes of a warp take the SAME 8-word group of 32
+// consecutive query rows, whose intervals nearly coincide, so a skipped word is skipped by the whole warp (with the
+// linear mapping the four lanes of a row look at four different key ranges and some lane always draws).
+template <bool kByRows>
 __global__ void attn_keep_mask_kernel(uint32_t* __restrict__ keep, long long n_words, uint32_t thr, uint32_t k0,
-                                      uint32_t k1) {
-  const long long w0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+                                      uint32_t k1, const int* __restrict__ row_lo, const int* __restrict__ row_hi,
+                                      int H, int T, int nw) {
+  long long w0;
+  if constexpr (kByRows) {
+    const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;  // global warp index
+    const int groups = nw >> 3;
+    const long long row = (gw / groups) * 32 + (threadIdx.x & 31);
+    w0 = row * nw + (gw % groups) * 8;
+    if (row * nw >= n_words) return;
+  } else {
+    w0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  }
   if (w0 >= n_words) return;
   uint32_t out[8];
+  long long cur_row = -1;
+  int lo = 0, hi = 0;
 #pragma unroll
-  for (int u = 0; u < 8; ++u) out[u] = keep_word_draw(k0, k1, static_cast<unsigned long long>(w0 + u), thr);
-  if (w0 + 8 <= n_words && (reinterpret_cast<uintptr_t>(keep + w0) & 15) == 0) {
-    reinterpret_cast<uint4*>(keep + w0)[0] = make_uint4(out[0], out[1], out[2], out[3]);
-    reinterpret_cast<uint4*>(keep + w0)[1] = make_uint4(out[4], out[5], out[6], out[7]);
+  for (int u = 0; u < 8; ++u) {
+    bool draw = true;
+    if (row_lo != nullptr && w0 + u < n_words) {
+      const long long row = (w0 + u) / nw;          // flat (b, h, i)
+      const int w = static_cast<int>((w0 + u) - row * nw);
+      if (row != cur_row) {
+        cur_row = row;
+        const long long b = row / (static_cast<long long>(H) * T);
+        const int i = static_cast<int>(row % T);
+        lo = row_lo[b * T + i];
+        hi = row_hi[b * T + i];
+      }
+      draw = (lo >= hi) || (w * 32 < hi && w * 32 + 32 > lo);
+    }
+    out[u] = draw ? keep_word_draw(k0, k1, static_cast<unsigned long long>(w0 + u), thr) : 0xffffffffu;
+  }
+  if (w0 + 8 <= n_words && (reinterpret_cast<uintptr_t>(keep + w0) & 31) == 0) {
+    st_global_256(keep + w0, out);  // one full 32-byte sector per lane
   } else {
 #pragma unroll
     for (int u = 0; u < 8; ++u)
@@ -61,7 +95,8 @@ __global__ void attn_keep_mask_kernel(uint32_t* __restrict__ keep, long long n_w
 using namespace obt;
 
 extern "C" int obt_attn_keep_mask(unsigned int* keep, int B, int H, int T, float drop_p, unsigned long long seed,
-                                  unsigned long long offset, cudaStream_t stream) {
+                                  unsigned long long offset, const int* row_lo, const int* row_hi,
+                                  cudaStream_t stream) {
   OBT_REQUIRE(keep != nullptr, "obt_attn_keep_mask: null pointer");
   OBT_REQUIRE(B > 0 && H > 0 && T > 0, "obt_attn_keep_mask: empty problem");
   OBT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "obt_attn_keep_mask: dropout p=%f", drop_p);
@@ -70,8 +105,18 @@ extern "C" int obt_attn_keep_mask(unsigned int* keep, int B, int H, int T, float
   if (thr > (1u << KEEP_PLANES) - 1u) thr = (1u << KEEP_PLANES) - 1u;
   const unsigned long long key = seed ^ (offset * 0xD1B54A32D192ED03ull);
   const int threads = 256;
-  const long long per_block = static_cast<long long>(threads) * 8;
-  attn_keep_mask_kernel<<<static_cast<unsigned>((n_words + per_block - 1) / per_block), threads, 0, stream>>>(
-      keep, n_words, thr, static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32));
+  const int nw = keep_words(T);
+  const int* lo = (row_lo != nullptr && row_hi != nullptr) ? row_lo : nullptr;
+  const long long n_rows = static_cast<long long>(B) * H * T;
+  if (lo != nullptr && nw % 8 == 0) {
+    // warps = ceil(rows / 32) * (nw / 8); 8 warps per block
+    const long long warps = (n_rows + 31) / 32 * (nw / 8);
+    attn_keep_mask_kernel<true><<<static_cast<unsigned>((warps + 7) / 8), threads, 0, stream>>>(
+        keep, n_words, thr, static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), lo, row_hi, H, T, nw);
+  } else {
+    const long long per_block = static_cast<long long>(threads) * 8;
+    attn_keep_mask_kernel<false><<<static_cast<unsigned>((n_words + per_block - 1) / per_block), threads, 0, stream>>>(
+        keep, n_words, thr, static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), lo, row_hi, H, T, nw);
+  }
   return check_launch("attn_keep_mask");
 }

@@ -140,7 +140,7 @@ class BlockFunction(torch.autograd.Function):
         h1, _, mean1, rstd1 = ops.layernorm_fwd(x, g1)
         # c_attn with the rotary embedding of q and k fused into the GEMM epilogue (model.py:102-108)
         qkv = ops.gemm(h1, w_qkv, epilogue=ops.EPI_ROPE, rope=(cos_tab, sin_tab, T, d, 2 * C))
-        keep = ops.attn_keep_mask(B, H, T, p, *seeds[0], dev) if p > 0.0 else None
+        keep = ops.attn_keep_mask(B, H, T, p, *seeds[0], dev, mask) if p > 0.0 else None
         y, lse = ops.attention_fwd(qkv, B, T, H, d, scale, mask, p, keep)
         if p > 0.0:
             x1 = ops.gemm(y, w_o, epilogue=ops.EPI_RESID_DROPOUT, aux_in=x, drop_p=p, seed=seeds[1][0], offset=seeds[1][1])

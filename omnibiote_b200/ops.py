@@ -327,11 +327,16 @@ def keep_words(T: int) -> int:
     return (T + 31) // 32
 
 
-def attn_keep_mask(B: int, H: int, T: int, drop_p: float, seed: int, offset: int, device) -> torch.Tensor:
+def attn_keep_mask(B: int, H: int, T: int, drop_p: float, seed: int, offset: int, device,
+                   mask: "MaskSpec | None" = None) -> torch.Tensor:
     """Attention-dropout keep bits [B,H,T,ceil(T/32)] (int32 words, bit layout: csrc/dropmask.cuh) for one layer and
-    micro-batch, drawn once and read by the forward, dQ and dK/dV kernels."""
+    micro-batch, drawn once and read by the forward, dQ and dK/dV kernels. With an interval `mask`, words of a row that
+    lie entirely outside its visible interval are stored as all-ones instead of being drawn."""
     keep = torch.empty((B, H, T, keep_words(T)), dtype=torch.int32, device=device)
-    rc = _lib.load().obt_attn_keep_mask(keep.data_ptr(), B, H, T, float(drop_p), seed, offset, _stream())
+    use_iv = mask is not None and mask.tensor is None and mask.row_lo is not None
+    rc = _lib.load().obt_attn_keep_mask(keep.data_ptr(), B, H, T, float(drop_p), seed, offset,
+                                        _ptr(mask.row_lo) if use_iv else 0, _ptr(mask.row_hi) if use_iv else 0,
+                                        _stream())
     _lib.check(rc, "obt_attn_keep_mask")
     return keep
 

@@ -30,7 +30,7 @@ def main():
     ids = torch.from_numpy(bench.synth_ids(B, T, np.random.RandomState(1234))).to(dev)
     lo, hi = ops.doc_mask_intervals(ids, 3, False)
     spec = ops.MaskSpec(None, B, H, T, lo, hi) if os.environ.get("PROBE_NOMASK") is None else ops.MaskSpec(None, B, H, T)
-    keep = ops.attn_keep_mask(B, H, T, p, 1, 0, dev) if p > 0 else None
+    keep = ops.attn_keep_mask(B, H, T, p, 1, 0, dev, spec) if p > 0 else None
 
     def timed(fn):
         for _ in range(min(10, max(3, reps // 4))):
@@ -46,7 +46,7 @@ def main():
 
     ms_f, (y, lse) = timed(lambda: ops.attention_fwd(qkv, B, T, H, d, scale, spec, p, keep, impl="tc"))
     ms_b, dqkv = timed(lambda: ops.attention_bwd(qkv, y, dy, lse, B, T, H, d, scale, spec, p, keep, impl="tc"))
-    ms_k, _ = timed(lambda: ops.attn_keep_mask(B, H, T, p, 1, 0, dev)) if p > 0 else (0.0, None)
+    ms_k, _ = timed(lambda: ops.attn_keep_mask(B, H, T, p, 1, 0, dev, spec)) if p > 0 else (0.0, None)
 
     # element check on batch row 0 against fp32 torch with the same keep mask
     b0 = slice(0, T)

@@ -202,6 +202,43 @@ def test_attn_dropout_same_mask_in_both_kernels_and_in_backward():
     assert rel_err(g_tc, g_si) < 2e-2
 
 
+@pytest.mark.parametrize("T", [1024, 512, 200])   # 1024 / 512: warp-per-32-rows mapping (nw % 8 == 0); 200: linear mapping
+def test_keep_mask_skips_words_outside_the_visible_interval(T):
+    """With an interval mask the generator stores all-ones for the 32-key words no key of which the row can see, and the
+    SAME bits as the full draw everywhere else; fully-masked rows (uniform attention over every key) are drawn in full.
+    Attention with either mask is bit-identical."""
+    from omnibiote_b200 import ops
+    B, H, d, p = 2, 2, 128, 0.1
+    C = H * d
+    ids = _doc_ids(B, T, T + 9)
+    ids[1, T - 40:] = 1
+    lo, hi = ops.doc_mask_intervals(ids, 3, True)
+    assert bool((lo >= hi).any())
+    spec = ops.MaskSpec(None, B, H, T, lo, hi)
+    full = ops.attn_keep_mask(B, H, T, p, 5, 16, "cuda")
+    part = ops.attn_keep_mask(B, H, T, p, 5, 16, "cuda", spec)
+    nw = full.shape[-1]
+    w = torch.arange(nw, device="cuda").view(1, 1, nw) * 32
+    dead = (lo >= hi).unsqueeze(-1)
+    visible = dead | ((w < hi.unsqueeze(-1)) & (w + 32 > lo.unsqueeze(-1)))       # [B,T,nw]
+    visible = visible.unsqueeze(1).expand(B, H, T, nw)
+    assert torch.equal(part[visible], full[visible])
+    assert bool((part[~visible] == -1).all())
+    assert 0.2 < float((~visible).float().mean()) < 0.95                            # the test really exercises both
+    torch.manual_seed(T)
+    qkv = (torch.randn(B * T, 3 * C, device="cuda") * 1.5).to(BF)
+    scale = 8.0 / C
+    y0, lse0 = ops.attention_fwd(qkv, B, T, H, d, scale, spec, p, full, impl="tc")
+    y1, lse1 = ops.attention_fwd(qkv, B, T, H, d, scale, spec, p, part, impl="tc")
+    assert torch.equal(y0, y1) and torch.equal(lse0, lse1)
+    dy = torch.randn(B * T, C, device="cuda").to(BF)
+    g0 = ops.attention_bwd(qkv, y0, dy, lse0, B, T, H, d, scale, spec, p, full, impl="tc")
+    g1 = ops.attention_bwd(qkv, y1, dy, lse1, B, T, H, d, scale, spec, p, part, impl="tc")
+    assert torch.equal(g0, g1)
+    # a dense-bias MaskSpec carries no intervals: full draw
+    assert torch.equal(ops.attn_keep_mask(B, H, T, p, 5, 16, "cuda", ops.MaskSpec(None, B, H, T)), full)
+
+
 def test_tile_metadata_of_interval_masks():
     """obt_attn_tile_meta against a torch restatement: per 128-query tile {min lo, max hi, any fully-masked row}, per
     128-key tile the relevance bits of the 64-query sub-tiles."""
