@@ -16,6 +16,7 @@ Keys beyond the base contract (all measured in this process, after the headline 
   roofline              per-GEMM CUDA events in a SEPARATE instrumented step (the timed `value` loop carries none)
   encode                BASELINE configs 1 / 5: encode() sequences/s at ctx 1024 and 4096 (all / max / mean), device
                         resident and end to end (pinned ids H2D, result D2H), + the CPU fp32 encode("mean") B=2 leg
+  dropin_module_loop    the nn.Module driven by the reference's own loop (dense bias, full logits, ATen CE, torch clip)
   gpu_eager_reference   the reference arithmetic (oracle restatement: torch eager, cuBLAS + SDPA, bf16) timed on the
                         same GPU for the same step schedule: the GPU bar the kernels are measured against
   cpu_baseline          the same on the host cores (bounded sample)
@@ -284,6 +285,61 @@ def gpu_eager_reference(device, cfg=SMALL, global_batch=1024, mbs=32, n_micro=3)
     return out
 
 
+def dropin_module_loop(device, cfg=SMALL, global_batch=1024, mbs=32, dropout=0.1, n_micro=3):
+    """The path the reference's OWN loop (train_encoder.py:270-318) takes through the drop-in nn.Module, without
+    MLMTrainer and without interval masks: a dense additive (b, n_head, t, t) bias handed to `model(idx, attn_mask)`
+    (read by every layer's attention kernel), the full (b, t, vocab) logits returned to the caller (4 GiB per
+    micro-batch), ATen `F.cross_entropy` + the mask / sum / div arithmetic in torch, `loss.backward()`, a
+    `loss.item()` per micro-batch, then torch's `clip_grad_norm_` and `MuAdamW.step()` / `zero_grad()`. The MLM draw and
+    the dense mask are built on the device (the reference's host loops are the caller's code, not the module's).
+    t_step = n_accum * mean(t_mb) + t_opt, wall clock with synchronize."""
+    import torch.nn.functional as F
+    from omnibiote_b200 import ops
+    from omnibiote_b200.optim import MuAdamW
+    from omnibiote_b200.train import mlm_mask
+    T, H, V = cfg["block_size"], cfg["n_head"], cfg["vocab_size"]
+    model = build_model(device, dropout, cfg)
+    model.train()
+    opt = MuAdamW(model.parameters(), lr=1e-2 * np.sqrt(global_batch) / 32, weight_decay=1e-2)
+    ids = torch.from_numpy(synth_ids(mbs, T, np.random.RandomState(5))).to(device)
+    n_accum = global_batch // mbs
+
+    def micro_batch():
+        masked, loss_mask = mlm_mask(ids, 0.15)
+        lo, hi = ops.doc_mask_intervals(ids, 3, False)
+        bias = ops.mask_from_intervals(lo, hi).unsqueeze(1).expand(-1, H, -1, -1)        # (b, n_head, t, t) bf16
+        logits = model(masked, attn_mask=bias)
+        ce = F.cross_entropy(logits.view(-1, V), ids.view(-1), reduction="none") / n_accum
+        ce = ce * loss_mask.view(-1).to(ce.dtype)
+        loss = ce.sum() / loss_mask.sum()
+        loss.backward()
+        return loss.item()
+
+    def optimizer():
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    micro_batch(); optimizer()                                      # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n_micro):
+        last = micro_batch()
+    torch.cuda.synchronize()
+    t_mb = (time.perf_counter() - t0) / n_micro
+    t0 = time.perf_counter()
+    optimizer()
+    torch.cuda.synchronize()
+    t_opt = time.perf_counter() - t0
+    t_step = n_accum * t_mb + t_opt
+    del model, opt
+    torch.cuda.empty_cache()
+    return {"value": global_batch * T / t_step, "unit": "tokens/s", "ms_per_micro_batch": t_mb * 1e3,
+            "ms_optimizer": t_opt * 1e3, "ms_per_step": t_step * 1e3, "loss": last,
+            "what": "omnibiote_b200.OmniBioTA driven like train_encoder.py:270-318: dense (b,h,t,t) bias per layer, full "
+                    "logits + ATen cross_entropy, loss.item() per micro-batch, torch clip_grad_norm_ + MuAdamW.step()"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -364,7 +420,7 @@ def time_steps(trainer, ids, steps, barrier):
     return ev0.elapsed_time(ev1), loss
 
 
-def encode_bench(device, reps=8):
+def encode_bench(device, reps=40):
     """BASELINE config 5 (+ the GPU side of config 1): eval(), encode() without attn_mask on variable-length PADDED
     batches; device-resident sequences/s and end-to-end (pinned ids H2D + result D2H inside the timed region)."""
     out = []
@@ -377,7 +433,7 @@ def encode_bench(device, reps=8):
         ftok = encode_flops_per_token(SMALL, T)
         for method in ("all", "max", "mean"):
             with torch.no_grad():
-                for _ in range(3):
+                for _ in range(10):  # also settles the power state: 8-rep timings drifted 15 % from first to last method
                     res = model.encode(ids, method)
                 host_out = torch.empty(res.shape, dtype=res.dtype).pin_memory()
                 torch.cuda.synchronize()
@@ -553,6 +609,11 @@ def run_b200(args):
                 extras["gpu_eager_reference"] = gpu_eager_reference(device, cfg, args.global_batch, mbs)
             except Exception as e:
                 extras["gpu_eager_reference"] = {"error": repr(e)[:300]}
+            try:
+                extras["dropin_module_loop"] = dropin_module_loop(device, cfg, args.global_batch, mbs, args.dropout)
+            except Exception as e:
+                extras["dropin_module_loop"] = {"error": repr(e)[:300]}
+                torch.cuda.empty_cache()
         if world == 8 and not args.skip_large:
             try:
                 res = run_large_extra(device, world, rank, barrier)

@@ -50,36 +50,43 @@ template <bool kByRows>
 __global__ void attn_keep_mask_kernel(uint32_t* __restrict__ keep, long long n_words, uint32_t thr, uint32_t k0,
                                       uint32_t k1, const int* __restrict__ row_lo, const int* __restrict__ row_hi,
                                       int H, int T, int nw) {
+  uint32_t out[8];
   long long w0;
   if constexpr (kByRows) {
+    // division-free per word: (row, first word in row) known up front, one interval per lane
     const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;  // global warp index
     const int groups = nw >> 3;
-    const long long row = (gw / groups) * 32 + (threadIdx.x & 31);
-    w0 = row * nw + (gw % groups) * 8;
-    if (row * nw >= n_words) return;
+    const long long rblk = gw / groups;
+    const int wr = static_cast<int>(gw - rblk * groups) * 8;       // first word of this lane's group within its row
+    const long long row = rblk * 32 + (threadIdx.x & 31);          // flat (b, h, i)
+    w0 = row * nw + wr;
+    if (w0 >= n_words) return;
+    const long long b = row / (static_cast<long long>(H) * T);
+    const int i = static_cast<int>(row % T);
+    const int lo = row_lo[b * T + i], hi = row_hi[b * T + i];
+    const bool dead = lo >= hi;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = (wr + u) * 32;
+      const bool draw = dead || (k < hi && k + 32 > lo);
+      out[u] = draw ? keep_word_draw(k0, k1, static_cast<unsigned long long>(w0 + u), thr) : 0xffffffffu;
+    }
   } else {
     w0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
-  }
-  if (w0 >= n_words) return;
-  uint32_t out[8];
-  long long cur_row = -1;
-  int lo = 0, hi = 0;
+    if (w0 >= n_words) return;
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    bool draw = true;
-    if (row_lo != nullptr && w0 + u < n_words) {
-      const long long row = (w0 + u) / nw;          // flat (b, h, i)
-      const int w = static_cast<int>((w0 + u) - row * nw);
-      if (row != cur_row) {
-        cur_row = row;
+    for (int u = 0; u < 8; ++u) {
+      bool draw = true;
+      if (row_lo != nullptr && w0 + u < n_words) {  // odd shapes only (nw % 8 != 0): a division per word is fine
+        const long long row = (w0 + u) / nw;
+        const int w = static_cast<int>((w0 + u) - row * nw);
         const long long b = row / (static_cast<long long>(H) * T);
         const int i = static_cast<int>(row % T);
-        lo = row_lo[b * T + i];
-        hi = row_hi[b * T + i];
+        const int lo = row_lo[b * T + i], hi = row_hi[b * T + i];
+        draw = (lo >= hi) || (w * 32 < hi && w * 32 + 32 > lo);
       }
-      draw = (lo >= hi) || (w * 32 < hi && w * 32 + 32 > lo);
+      out[u] = draw ? keep_word_draw(k0, k1, static_cast<unsigned long long>(w0 + u), thr) : 0xffffffffu;
     }
-    out[u] = draw ? keep_word_draw(k0, k1, static_cast<unsigned long long>(w0 + u), thr) : 0xffffffffu;
   }
   if (w0 + 8 <= n_words && (reinterpret_cast<uintptr_t>(keep + w0) & 31) == 0) {
     st_global_256(keep + w0, out);  // one full 32-byte sector per lane

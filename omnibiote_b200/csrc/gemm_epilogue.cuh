@@ -191,9 +191,10 @@ struct EpiTraits {
 };
 
 // v: rb(acc) for 8 consecutive columns; a: aux_in values (when the epilogue has one). Returns D in v, U in u.
+// eidx: flat element index row * N + col of v[0] (the dropout stream is keyed by it).
 template <int EPI>
 __device__ __forceinline__ void epilogue_math(const GemmParams& p, float (&v)[8], const float (&a)[8], float (&u)[8],
-                                              long long grow, int gcol) {
+                                              unsigned long long eidx) {
   if constexpr (EPI == EPI_RESID) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = a[e] + v[e];
@@ -203,7 +204,7 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, float (&v)[8]
   } else if constexpr (EPI == EPI_RESID_DROPOUT) {
     // one RNG call per 4 consecutive columns, keyed by the flat element index row*N + col
     const float scale = 1.0f / (1.0f - p.drop_p);
-    const unsigned long long base = (static_cast<unsigned long long>(grow) * p.N + gcol) >> 2;
+    const unsigned long long base = eidx >> 2;
 #pragma unroll
     for (int j4 = 0; j4 < 2; ++j4) {
       const uint4 rnd = rand4x32(p.seed, base + j4, p.offset);
@@ -314,12 +315,81 @@ __device__ __noinline__ void epilogue_segment_slow(const GemmParams& p, uint4 w,
       for (int e = 0; e < 8; ++e) v[e] = 0.f;
     }
   }
-  epilogue_math<EPI>(p, v, a, u, grow, gcol);
+  epilogue_math<EPI>(p, v, a, u, static_cast<unsigned long long>(grow) * p.N + gcol);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     if (e < nvalid) {
       if constexpr (EpiTraits<EPI>::kAuxOut) p.aux_out[grow * p.ld_aux_out + gcol + e] = __float2bfloat16_rn(u[e]);
       p.D[grow * p.ldd + gcol + e] = __float2bfloat16_rn(v[e]);
+    }
+  }
+}
+
+// Interior fast path of one staged 32-row x 64-column chunk: every row and column is inside the matrix and 16-byte
+// aligned (warp-uniform test in the caller), so the 8 row-iterations carry NO branches and the compiler interleaves
+// the four iterations of a group (with the per-iteration bounds branches of the general path it emitted them one
+// after the other, each a dependent chain: `stall_wait` was the top stall of every second-operand epilogue,
+// profiles/r02n_gemm_epi5.source.txt). Row pointers and the dropout stream index advance by constants.
+template <int EPI>
+__device__ __forceinline__ void epilogue_rows_interior(const GemmParams& p, const uint8_t* stage, int lane,
+                                                       long long row_base, int col_base, const uint4 (&axs)[8],
+                                                       float (&dacc0)[4], float (&dacc1)[4]) {
+  const int rsub = lane >> 3, seg = lane & 7;
+  const int gcol = col_base + seg * 8;
+  const long long row0 = row_base + rsub;
+  __nv_bfloat16* drow = p.D + row0 * p.ldd + gcol;
+  __nv_bfloat16* urow = nullptr;
+  if constexpr (EpiTraits<EPI>::kAuxOut) urow = p.aux_out + row0 * p.ld_aux_out + gcol;
+  unsigned long long eidx = static_cast<unsigned long long>(row0) * p.N + gcol;
+  const unsigned long long estep = 4ull * p.N;                         // 4 rows further per iteration
+  const bool rope_chunk = (EPI == EPI_ROPE) && col_base < p.rope_cols;  // chunk-uniform: rope_cols % 64 == 0
+  const unsigned char* rmask = reinterpret_cast<const unsigned char*>(p.aux_in);
+#pragma unroll 1
+  for (int hf = 0; hf < 2; ++hf) {
+    uint4 w[4];
+    float4 rc[4], rs[4];
+    unsigned char rm[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rl = (hf * 4 + it) * 4 + rsub;
+      w[it] = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((seg ^ (rl & 7)) << 4));
+      if constexpr (EPI == EPI_ROPE) {
+        rc[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+        rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rope_chunk) {
+          const long long off = rope_table_off(p, row_base + rl, gcol);
+          rc[it] = *reinterpret_cast<const float4*>(p.rope_cos + off);
+          if (p.rope_sin != nullptr) rs[it] = *reinterpret_cast<const float4*>(p.rope_sin + off);
+        }
+      }
+      if constexpr (EPI == EPI_ROWMASK) rm[it] = rmask[row_base + rl];
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      float v[8], a[8], u[8];
+      unpack8f(w[it], v);
+      if constexpr (EpiTraits<EPI>::kAuxIn) unpack8f(hf == 0 ? axs[it] : axs[4 + it], a);
+      if constexpr (EPI == EPI_ROPE) {
+        if (rope_chunk) rope8(v, rc[it], rs[it], p.rope_sin != nullptr, false);
+      }
+      if constexpr (EPI == EPI_ROWMASK) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = rm[it] != 0 ? v[e] : 0.f;
+      }
+      if constexpr (EPI == EPI_DELTA) {
+        float d8 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d8 = fmaf(v[e], a[e], d8);
+        if (hf == 0) dacc0[it] += d8; else dacc1[it] += d8;
+      }
+      epilogue_math<EPI>(p, v, a, u, eidx);
+      eidx += estep;
+      if constexpr (EpiTraits<EPI>::kAuxOut) {
+        *reinterpret_cast<uint4*>(urow) = pack8f(u);
+        urow += 4 * p.ld_aux_out;
+      }
+      *reinterpret_cast<uint4*>(drow) = pack8f(v);
+      drow += 4 * p.ldd;
     }
   }
 }
@@ -369,42 +439,38 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
       stage_write_bf16(stage, lane, r0, r1);
       __syncwarp();
       const int gcol = col_base + seg * 8;
-      const bool col_ok = gcol < p.N;
-      const bool vec = p.vec_ok && (p.N - gcol >= 8);
-      // two groups of 4 row-iterations (keeps the unrolled code of each epilogue variant within the I-cache)
+      // warp-uniform: the whole 32 x 64 chunk inside the matrix, 16-byte accesses allowed
+      bool interior = p.vec_ok && (col_base + 64 <= p.N) && (row_base + 32 <= p.M);
+      if constexpr (EPI == EPI_ROPE) interior = interior && ((p.rope_cols & 63) == 0);
+      if (interior) {
+        epilogue_rows_interior<EPI>(p, stage, lane, row_base, col_base, axs, dacc0, dacc1);
+      } else {
+        // matrix edges (ragged M / N, unaligned pointers): one row-iteration at a time with bounds checks
+        const bool col_ok = gcol < p.N;
+        const bool vec = p.vec_ok && (p.N - gcol >= 8);
 #pragma unroll 1
-      for (int hf = 0; hf < 2; ++hf) {
-        uint4 w[4], ax[4];
-        float4 rc[4], rs[4];
-        // staged values and aux loads of the group first (independent loads in flight together) ...
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int rl = (hf * 4 + it) * 4 + rsub;
-          w[it] = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((seg ^ (rl & 7)) << 4));
-          if constexpr (EPI == EPI_ROPE) {
-            const long long grow = row_base + rl;
-            rc[it] = make_float4(1.f, 1.f, 1.f, 1.f);
-            rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (grow < p.M && gcol < p.rope_cols) {
-              const long long off = rope_table_off(p, grow, gcol);
-              rc[it] = *reinterpret_cast<const float4*>(p.rope_cos + off);
-              if (p.rope_sin != nullptr) rs[it] = *reinterpret_cast<const float4*>(p.rope_sin + off);
-            }
-          }
-          if constexpr (EpiTraits<EPI>::kAuxIn) ax[it] = hf == 0 ? axs[it] : axs[4 + it];
-        }
-        // ... then the math and the stores
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int rl = (hf * 4 + it) * 4 + rsub;
+        for (int it8 = 0; it8 < 8; ++it8) {
+          const int rl = it8 * 4 + rsub;
           const long long grow = row_base + rl;
+          const uint4 w = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((seg ^ (rl & 7)) << 4));
           if (grow < p.M && col_ok) {
             if (vec) {
               float v[8], a[8], u[8];
-              unpack8f(w[it], v);
-              if constexpr (EpiTraits<EPI>::kAuxIn) unpack8f(ax[it], a);
+              unpack8f(w, v);
+              if constexpr (EpiTraits<EPI>::kAuxIn) {
+                uint4 ax = axs[0];  // register array: select without dynamic indexing
+#pragma unroll
+                for (int k = 1; k < 8; ++k) ax = it8 == k ? axs[k] : ax;
+                unpack8f(ax, a);
+              }
               if constexpr (EPI == EPI_ROPE) {
-                if (gcol < p.rope_cols) rope8(v, rc[it], rs[it], p.rope_sin != nullptr, false);
+                if (gcol < p.rope_cols) {
+                  const long long off = rope_table_off(p, grow, gcol);
+                  const float4 rc = *reinterpret_cast<const float4*>(p.rope_cos + off);
+                  float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (p.rope_sin != nullptr) rs = *reinterpret_cast<const float4*>(p.rope_sin + off);
+                  rope8(v, rc, rs, p.rope_sin != nullptr, false);
+                }
               }
               if constexpr (EPI == EPI_ROWMASK) {
                 if (reinterpret_cast<const unsigned char*>(p.aux_in)[grow] == 0) {
@@ -416,14 +482,18 @@ __device__ __forceinline__ void epilogue_chunks(const GemmParams& p, uint32_t ta
                 float d8 = 0.f;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) d8 = fmaf(v[e], a[e], d8);
-                if (hf == 0) dacc0[it] += d8; else dacc1[it] += d8;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (it8 == k) dacc0[k] += d8;
+                  if (it8 == 4 + k) dacc1[k] += d8;
+                }
               }
-              epilogue_math<EPI>(p, v, a, u, grow, gcol);
+              epilogue_math<EPI>(p, v, a, u, static_cast<unsigned long long>(grow) * p.N + gcol);
               if constexpr (EpiTraits<EPI>::kAuxOut)
                 *reinterpret_cast<uint4*>(p.aux_out + grow * p.ld_aux_out + gcol) = pack8f(u);
               *reinterpret_cast<uint4*>(p.D + grow * p.ldd + gcol) = pack8f(v);
             } else {
-              epilogue_segment_slow<EPI>(p, w[it], grow, gcol);
+              epilogue_segment_slow<EPI>(p, w, grow, gcol);
             }
           }
         }

@@ -378,8 +378,16 @@ __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
 }
 __device__ __forceinline__ uint64_t f2_splat(float x) { return f2_pack(x, x); }
 
-// round an fp32 value to bf16 (RNE) and return it widened back to fp32
-__device__ __forceinline__ float rb(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// round an fp32 value to bf16 (RNE) and return it widened back to fp32. ONE packed conversion with a zero low half:
+// the 32-bit result (bf16(x) << 16) already is the fp32 bit pattern. `__float2bfloat16_rn` + widening compiles to
+// F2F.BF16.F32 (conversion unit: variable latency, a fraction of the FP32 rate; its short-scoreboard waits were the
+// top stall of the GEMM's dropout epilogue and ~10 per element sit in the AdamW kernel, profiles/r02n_*) plus a shift;
+// this form is a single fixed-latency F2FP.BF16.F32.PACK_AB on the ALU pipe. Same RNE, same canonical NaN.
+__device__ __forceinline__ float rb(float x) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x), "f"(0.f));
+  return __uint_as_float(r);
+}
 
 // Philox4x32-10 counter RNG: (seed, subsequence=index/4, offset) -> 4 x 32 random bits.
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t subseq, uint64_t offset) {

@@ -18,6 +18,7 @@ Differences from the reference's schedule that do not change the arithmetic cont
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -85,7 +86,7 @@ class MLMTrainer:
         dev = next(model.parameters()).device
         self.process_group = process_group
         self.comm_stream = torch.cuda.Stream() if (self.world > 1 and dev.type == "cuda") else None
-        self.buckets = FlatGradBuckets(model_buckets(model), process_group, self.comm_stream)
+        self.buckets = FlatGradBuckets(model_buckets(model), self._gradient_group(process_group, dev), self.comm_stream)
         # per-step bookkeeping on the device: [loss_sum, n_masked, n_tokens] of this rank, two rotating buffers (the
         # all-reduce of step k runs behind the optimizer of step k and is only waited for at step k+1's gradient sync)
         self._stats_buf = [torch.zeros(3, dtype=torch.float32, device=dev) for _ in range(2)]
@@ -95,6 +96,18 @@ class MLMTrainer:
         self.tokens_seen = torch.zeros(1, dtype=torch.float64, device=dev)  # cumulative non-PAD tokens, all ranks
         self.n_steps = 0
         self.trained_tokens = 0  # host-side count of token POSITIONS (global_batch * ctx_len per step)
+
+    def _gradient_group(self, process_group, dev):
+        """Communicator of the gradient all-reduce. The compute kernels are persistent and fill every SM, so a NCCL kernel
+        enqueued during the backward only gets SMs at a kernel boundary, where it competes with the next compute kernel;
+        on a default-priority stream it mostly lost and the all-reduce ran AFTER the backward (exposed wait ~ the whole
+        all-reduce: profiles/r02m_*). A dedicated NCCL communicator whose internal stream is high priority wins those
+        boundaries. OBT_NCCL_HIGH_PRIORITY=0 keeps the caller's group."""
+        if (self.world <= 1 or dev.type != "cuda" or process_group is not None
+                or os.environ.get("OBT_NCCL_HIGH_PRIORITY", "1") == "0" or dist.get_backend() != "nccl"):
+            return process_group
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        return dist.new_group(backend="nccl", pg_options=opts)
 
     def step(self, input_ids: torch.Tensor) -> torch.Tensor:
         """input_ids: this rank's (batch_size, ctx_len) int64 token ids on the device.

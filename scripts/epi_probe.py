@@ -19,7 +19,12 @@ cases = {
     "gelu": dict(epilogue=ops.EPI_GELU, aux_out=u),
     "gelu_bwd": dict(epilogue=ops.EPI_GELU_BWD, aux_in=aux),
     "resid_dropout": dict(epilogue=ops.EPI_RESID_DROPOUT, aux_in=aux, drop_p=0.1, seed=1, offset=0),
+    "mul": dict(epilogue=ops.EPI_MUL, aux_in=aux),
+    "gelu_dg": dict(epilogue=ops.EPI_GELU_DG, aux_out=u),
 }
+if N % 128 == 0 and M % 1024 == 0:
+    cases["delta"] = dict(epilogue=ops.EPI_DELTA, aux_in=aux,
+                          delta=(torch.empty(M // 1024, N // 128, 1024, device="cuda"), 1024))
 for name, kw in cases.items():
     if only and name != only:
         continue
