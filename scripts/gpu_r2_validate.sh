@@ -30,4 +30,8 @@ timeout -k 10 600 ncu --set full --clock-control none -k regex:'ln_bwd_kernel|ad
   --skip-masked-rows-head --skip-extras > gpurun_out/${TAG}_ncu_rowwise.log 2>&1
 echo "ncu rowwise exit $?"
 ncu -i gpurun_out/${TAG}_rowwise.ncu-rep --page details > gpurun_out/${TAG}_rowwise.details.txt 2>&1
+PROBE_REPS=1 timeout -k 10 600 ncu --set full --clock-control none -k regex:'attn_tc|attn_keep_mask' -s 4 -c 6 -f \
+  -o gpurun_out/${TAG}_attn python scripts/attn_probe.py > gpurun_out/${TAG}_ncu_attn.log 2>&1
+echo "ncu attn exit $?"
+ncu -i gpurun_out/${TAG}_attn.ncu-rep --page details > gpurun_out/${TAG}_attn.details.txt 2>&1
 du -sh gpurun_out
