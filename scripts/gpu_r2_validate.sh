@@ -34,4 +34,7 @@ PROBE_REPS=1 timeout -k 10 600 ncu --set full --clock-control none -k regex:'att
   -o gpurun_out/${TAG}_attn python scripts/attn_probe.py > gpurun_out/${TAG}_ncu_attn.log 2>&1
 echo "ncu attn exit $?"
 ncu -i gpurun_out/${TAG}_attn.ncu-rep --page details > gpurun_out/${TAG}_attn.details.txt 2>&1
+PROBE_REPS=1 timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:attn_keep_mask -s 1 -c 1 -f \
+  -o gpurun_out/${TAG}_keepmask python scripts/attn_probe.py > gpurun_out/${TAG}_ncu_keepmask.log 2>&1
+ncu -i gpurun_out/${TAG}_keepmask.ncu-rep --page details > gpurun_out/${TAG}_keepmask.details.txt 2>&1
 du -sh gpurun_out
