@@ -53,16 +53,16 @@ __global__ void attn_keep_mask_kernel(uint32_t* __restrict__ keep, long long n_w
   uint32_t out[8];
   long long w0;
   if constexpr (kByRows) {
-    // division-free per word: (row, first word in row) known up front, one interval per lane
-    const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;  // global warp index
+    // grid (warp groups of one (b, h), B * H): no 64-bit division anywhere (the emulated divisions of a flat index
+    // were 45 % of the kernel's stall samples, profiles/r02s_keepmask.details.txt); one interval per lane
     const int groups = nw >> 3;
-    const long long rblk = gw / groups;
-    const int wr = static_cast<int>(gw - rblk * groups) * 8;       // first word of this lane's group within its row
-    const long long row = rblk * 32 + (threadIdx.x & 31);          // flat (b, h, i)
-    w0 = row * nw + wr;
-    if (w0 >= n_words) return;
-    const long long b = row / (static_cast<long long>(H) * T);
-    const int i = static_cast<int>(row % T);
+    const int wl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // warp within this (b, h)
+    const int rblk = wl / groups;                                        // 32-bit, warp-uniform
+    const int wr = (wl - rblk * groups) * 8;       // first word of this lane's group within its row
+    const int i = rblk * 32 + (threadIdx.x & 31);  // query row
+    if (i >= T) return;
+    const int bh = blockIdx.y, b = bh / H;
+    w0 = (static_cast<long long>(bh) * T + i) * nw + wr;
     const int lo = row_lo[b * T + i], hi = row_hi[b * T + i];
     const bool dead = lo >= hi;
 #pragma unroll
@@ -114,11 +114,10 @@ extern "C" int obt_attn_keep_mask(unsigned int* keep, int B, int H, int T, float
   const int threads = 256;
   const int nw = keep_words(T);
   const int* lo = (row_lo != nullptr && row_hi != nullptr) ? row_lo : nullptr;
-  const long long n_rows = static_cast<long long>(B) * H * T;
-  if (lo != nullptr && nw % 8 == 0) {
-    // warps = ceil(rows / 32) * (nw / 8); 8 warps per block
-    const long long warps = (n_rows + 31) / 32 * (nw / 8);
-    attn_keep_mask_kernel<true><<<static_cast<unsigned>((warps + 7) / 8), threads, 0, stream>>>(
+  if (lo != nullptr && nw % 8 == 0 && static_cast<long long>(B) * H < 65536) {
+    // per (b, h): (T / 32) row blocks x (nw / 8) word groups, one warp each; 8 warps per block
+    const int warps = (T / 32) * (nw / 8);
+    attn_keep_mask_kernel<true><<<dim3((warps + 7) / 8, B * H), threads, 0, stream>>>(
         keep, n_words, thr, static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), lo, row_hi, H, T, nw);
   } else {
     const long long per_block = static_cast<long long>(threads) * 8;

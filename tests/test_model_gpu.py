@@ -136,7 +136,7 @@ def test_clip_and_muadamw_step_matches_reference(golden):
         report[n] = rel_err(upd, ref)
     print("update rel err", {k: f"{v:.3f}" for k, v in report.items()})
     for n, p in model.named_parameters():
-        assert report[n] < 0.15, (n, report[n])
+        assert report[n] < 0.02, (n, report[n])  # measured on B200: <= 0.004 (profiles/r02s_tolerances.log)
         assert max_abs(p, c["params_after_step"][n]) <= 2 ** -6 * float(c["params_after_step"][n].abs().max()), n
 
 
