@@ -39,54 +39,57 @@ __device__ __forceinline__ uint32_t keep_word_draw(uint32_t k0, uint32_t k1, uns
   return ~lt;  // keep <=> u >= thr
 }
 
-// grid.x covers the B*H*T*nw words, 8 consecutive words (256 keys of one query row) per thread.
 // With an interval mask (row_lo / row_hi, int32 [B,T]) the words of a row that lie entirely outside its visible interval
 // are not drawn but stored as all-ones: every consumer multiplies those bits with an exactly-zero probability, and with
-// packed documents they are ~60 % of the matrix (the kernel is ALU-bound). Fully-masked rows (lo >= hi) attend to
-// every key and are drawn completely. kByRows (nw % 8 == 0): the 32 lanes of a warp take the SAME 8-word group of 32
-// consecutive query rows, whose intervals nearly coincide, so a skipped word is skipped by the whole warp (with the
-// linear mapping the four lanes of a row look at four different key ranges and some lane always draws).
-template <bool kByRows>
+// packed documents they are ~60 % of the matrix. Fully-masked rows (lo >= hi) attend to every key and are drawn
+// completely. The 32 lanes of a warp take the SAME 4-word group (128 keys) of 32 consecutive query rows, whose
+// intervals nearly coincide, so a skipped word is skipped by the whole warp (with a linear mapping the lanes of a row
+// look at different key ranges and some lane always draws). Grid (warp groups of one (b, h), B * H): no 64-bit index
+// arithmetic. The kernel is bound by the integer ALU pipe (LOP3 / SHF / SEL at half the issue rate,
+// profiles/r02s_keepmask.details.txt); 4 words per lane instead of 8 halves the work of the last wave.
+__global__ void attn_keep_mask_rows_kernel(uint32_t* __restrict__ keep, uint32_t thr, uint32_t k0, uint32_t k1,
+                                           const int* __restrict__ row_lo, const int* __restrict__ row_hi, int H, int T,
+                                           int nw) {
+  const int groups = nw >> 2;
+  const int wl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // warp within this (b, h)
+  const int rblk = wl / groups;                                        // warp-uniform
+  const int wr = (wl - rblk * groups) * 4;       // first word of this lane's group within its row
+  const int i = rblk * 32 + (threadIdx.x & 31);  // query row
+  if (i >= T) return;
+  const int bh = blockIdx.y, b = bh / H;
+  const long long w0 = (static_cast<long long>(bh) * T + i) * nw + wr;
+  const int lo = row_lo[b * T + i], hi = row_hi[b * T + i];
+  const bool dead = lo >= hi;
+  uint32_t out[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int k = (wr + u) * 32;
+    const bool draw = dead || (k < hi && k + 32 > lo);
+    out[u] = draw ? keep_word_draw(k0, k1, static_cast<unsigned long long>(w0 + u), thr) : 0xffffffffu;
+  }
+  *reinterpret_cast<uint4*>(keep + w0) = make_uint4(out[0], out[1], out[2], out[3]);  // nw % 4 == 0: 16-byte aligned
+}
+
+// Linear mapping (no interval mask, or a row length that is not a multiple of 128 keys): grid.x covers the B*H*T*nw
+// words, 8 consecutive words per thread.
 __global__ void attn_keep_mask_kernel(uint32_t* __restrict__ keep, long long n_words, uint32_t thr, uint32_t k0,
                                       uint32_t k1, const int* __restrict__ row_lo, const int* __restrict__ row_hi,
                                       int H, int T, int nw) {
   uint32_t out[8];
-  long long w0;
-  if constexpr (kByRows) {
-    // grid (warp groups of one (b, h), B * H): no 64-bit division anywhere (the emulated divisions of a flat index
-    // were 45 % of the kernel's stall samples, profiles/r02s_keepmask.details.txt); one interval per lane
-    const int groups = nw >> 3;
-    const int wl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // warp within this (b, h)
-    const int rblk = wl / groups;                                        // 32-bit, warp-uniform
-    const int wr = (wl - rblk * groups) * 8;       // first word of this lane's group within its row
-    const int i = rblk * 32 + (threadIdx.x & 31);  // query row
-    if (i >= T) return;
-    const int bh = blockIdx.y, b = bh / H;
-    w0 = (static_cast<long long>(bh) * T + i) * nw + wr;
-    const int lo = row_lo[b * T + i], hi = row_hi[b * T + i];
-    const bool dead = lo >= hi;
+  const long long w0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (w0 >= n_words) return;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int k = (wr + u) * 32;
-      const bool draw = dead || (k < hi && k + 32 > lo);
-      out[u] = draw ? keep_word_draw(k0, k1, static_cast<unsigned long long>(w0 + u), thr) : 0xffffffffu;
+  for (int u = 0; u < 8; ++u) {
+    bool draw = true;
+    if (row_lo != nullptr && w0 + u < n_words) {  // odd shapes only: a division per word is fine
+      const long long row = (w0 + u) / nw;
+      const int w = static_cast<int>((w0 + u) - row * nw);
+      const long long b = row / (static_cast<long long>(H) * T);
+      const int i = static_cast<int>(row % T);
+      const int lo = row_lo[b * T + i], hi = row_hi[b * T + i];
+      draw = (lo >= hi) || (w * 32 < hi && w * 32 + 32 > lo);
     }
-  } else {
-    w0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
-    if (w0 >= n_words) return;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      bool draw = true;
-      if (row_lo != nullptr && w0 + u < n_words) {  // odd shapes only (nw % 8 != 0): a division per word is fine
-        const long long row = (w0 + u) / nw;
-        const int w = static_cast<int>((w0 + u) - row * nw);
-        const long long b = row / (static_cast<long long>(H) * T);
-        const int i = static_cast<int>(row % T);
-        const int lo = row_lo[b * T + i], hi = row_hi[b * T + i];
-        draw = (lo >= hi) || (w * 32 < hi && w * 32 + 32 > lo);
-      }
-      out[u] = draw ? keep_word_draw(k0, k1, static_cast<unsigned long long>(w0 + u), thr) : 0xffffffffu;
-    }
+    out[u] = draw ? keep_word_draw(k0, k1, static_cast<unsigned long long>(w0 + u), thr) : 0xffffffffu;
   }
   if (w0 + 8 <= n_words && (reinterpret_cast<uintptr_t>(keep + w0) & 31) == 0) {
     st_global_256(keep + w0, out);  // one full 32-byte sector per lane
@@ -114,14 +117,15 @@ extern "C" int obt_attn_keep_mask(unsigned int* keep, int B, int H, int T, float
   const int threads = 256;
   const int nw = keep_words(T);
   const int* lo = (row_lo != nullptr && row_hi != nullptr) ? row_lo : nullptr;
-  if (lo != nullptr && nw % 8 == 0 && static_cast<long long>(B) * H < 65536) {
-    // per (b, h): (T / 32) row blocks x (nw / 8) word groups, one warp each; 8 warps per block
-    const int warps = (T / 32) * (nw / 8);
-    attn_keep_mask_kernel<true><<<dim3((warps + 7) / 8, B * H), threads, 0, stream>>>(
-        keep, n_words, thr, static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), lo, row_hi, H, T, nw);
+  if (lo != nullptr && nw % 4 == 0 && T % 32 == 0 && static_cast<long long>(B) * H < 65536 &&
+      (reinterpret_cast<uintptr_t>(keep) & 15) == 0) {
+    // per (b, h): (T / 32) row blocks x (nw / 4) word groups, one warp each; 8 warps per block
+    const int warps = (T / 32) * (nw / 4);
+    attn_keep_mask_rows_kernel<<<dim3((warps + 7) / 8, B * H), threads, 0, stream>>>(
+        keep, thr, static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), lo, row_hi, H, T, nw);
   } else {
     const long long per_block = static_cast<long long>(threads) * 8;
-    attn_keep_mask_kernel<false><<<static_cast<unsigned>((n_words + per_block - 1) / per_block), threads, 0, stream>>>(
+    attn_keep_mask_kernel<<<static_cast<unsigned>((n_words + per_block - 1) / per_block), threads, 0, stream>>>(
         keep, n_words, thr, static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), lo, row_hi, H, T, nw);
   }
   return check_launch("attn_keep_mask");

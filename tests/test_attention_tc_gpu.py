@@ -202,7 +202,7 @@ def test_attn_dropout_same_mask_in_both_kernels_and_in_backward():
     assert rel_err(g_tc, g_si) < 2e-2
 
 
-@pytest.mark.parametrize("T", [1024, 512, 200])   # 1024 / 512: warp-per-32-rows mapping (nw % 8 == 0); 200: linear mapping
+@pytest.mark.parametrize("T", [1024, 512, 200])   # 1024 / 512: warp per 32 rows x 4 words; 200: linear mapping
 def test_keep_mask_skips_words_outside_the_visible_interval(T):
     """With an interval mask the generator stores all-ones for the 32-key words no key of which the row can see, and the
     SAME bits as the full draw everywhere else; fully-masked rows (uniform attention over every key) are drawn in full.
