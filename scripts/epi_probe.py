@@ -22,6 +22,9 @@ cases = {
     "mul": dict(epilogue=ops.EPI_MUL, aux_in=aux),
     "gelu_dg": dict(epilogue=ops.EPI_GELU_DG, aux_out=u),
 }
+if N % 384 == 0 and M % 1024 == 0:  # c_attn: rotary (cosine-scaling form of a bf16 model) on the q | k two thirds
+    cos = torch.rand(1024, 64, device="cuda")
+    cases["rope"] = dict(epilogue=ops.EPI_ROPE, rope=(cos, None, 1024, 128, 2 * N // 3))
 if N % 128 == 0 and M % 1024 == 0:
     cases["delta"] = dict(epilogue=ops.EPI_DELTA, aux_in=aux,
                           delta=(torch.empty(M // 1024, N // 128, 1024, device="cuda"), 1024))
